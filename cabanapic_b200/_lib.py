@@ -1,0 +1,329 @@
+"""ctypes binding of the C ABI in include/cabanapic_b200.h.
+
+This is plumbing for tests and bench.py: the product is the shared library
+(``cabanapic_b200/libcabanapic_b200.so``, built from ``csrc/`` for sm_100a) and
+its C++ host facade (``include/cabanapic/``).  Nothing here computes anything;
+if the library is missing or no CUDA device is usable we fail loudly -- there
+is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcabanapic_b200.so")
+
+CONST_NAMES = "qdt_2mc cdt_dx cdt_dy cdt_dz qsp dx dy dz dt px py pz dt_eps0".split()
+PARTICLE_NAMES = "dx dy dz ux uy uz w cell".split()
+FIELD_NAMES = "ex ey ez cbx cby cbz jfx jfy jfz".split()
+
+SOLVER_EM, SOLVER_ES_1D = 0, 1
+BOUNDARY_REFLECT, BOUNDARY_PERIODIC = 0, 1
+FP_STRICT, FP_CONTRACT = 0, 1
+DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_ATOMIC_V4, DEPOSIT_WARP = 0, 1, 2, 3
+
+ERROR_NAMES = {-1: "CPIC_E_INVALID", -2: "CPIC_E_CUDA", -3: "CPIC_E_NOMEM", -4: "CPIC_E_CAPACITY",
+               -5: "CPIC_E_BAD_CELL", -6: "CPIC_E_UNSUPPORTED"}
+
+
+class CpicError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("ng", C.c_int32),
+                ("real_bytes", C.c_int32), ("solver", C.c_int32), ("boundary", C.c_int32), ("device", C.c_int32),
+                ("fp_mode", C.c_int32), ("deposit_mode", C.c_int32), ("max_particles", C.c_int64),
+                ("enable_sort", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class Consts(C.Structure):
+    _fields_ = [(n, C.c_double) for n in CONST_NAMES]
+
+    @classmethod
+    def from_dict(cls, d):
+        return cls(**{n: float(d[n]) for n in CONST_NAMES})
+
+    def to_dict(self):
+        return {n: getattr(self, n) for n in CONST_NAMES}
+
+
+class PushStats(C.Structure):
+    _fields_ = [("movers", C.c_int64), ("crossings", C.c_int64), ("wraps", C.c_int64 * 6)]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/ into the in-tree shared library (nvcc, sm_100a)."""
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libcabanapic_b200.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded C-ABI library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no fallback implementation)")
+        L = C.CDLL(LIB_PATH)
+        L.cpic_last_error.restype = C.c_char_p
+        L.cpic_last_error.argtypes = [C.c_void_p]
+        L.cpic_destroy.restype = None
+        L.cpic_destroy.argtypes = [C.c_void_p]
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        sig = {
+            "cpic_abi_version": [],
+            "cpic_create": [C.POINTER(Params), C.POINTER(vp)],
+            "cpic_sync": [vp],
+            "cpic_num_cells": [vp, C.POINTER(i64)],
+            "cpic_num_particles": [vp, C.POINTER(i64)],
+            "cpic_upload_particles": [vp] + [vp] * 8 + [i64],
+            "cpic_download_particles": [vp] + [vp] * 8 + [i64, C.POINTER(i64)],
+            "cpic_upload_fields": [vp, C.POINTER(vp)],
+            "cpic_download_fields": [vp, C.POINTER(vp)],
+            "cpic_upload_interpolators": [vp, vp],
+            "cpic_download_interpolators": [vp, vp],
+            "cpic_upload_accumulators": [vp, vp],
+            "cpic_download_accumulators": [vp, vp],
+            "cpic_load_interpolator_array": [vp],
+            "cpic_initialize_interpolator": [vp],
+            "cpic_clear_accumulator_array": [vp],
+            "cpic_push": [vp, C.POINTER(Consts)],
+            "cpic_contribute": [vp],
+            "cpic_unload_accumulator_array": [vp, C.POINTER(Consts)],
+            "cpic_advance_b": [vp, dbl, dbl, dbl],
+            "cpic_advance_e": [vp, dbl, dbl, dbl, dbl],
+            "cpic_uncenter_particles": [vp, dbl],
+            "cpic_energies": [vp, C.POINTER(dbl), C.POINTER(dbl)],
+            "cpic_update_ghosts": [vp, C.c_int],
+            "cpic_step": [vp, C.POINTER(Consts), i64, i32, vp],
+            "cpic_sort_particles": [vp],
+            "cpic_init_uniform_plasma": [vp, i64, i64, i32, i32, i32, i32, i32, C.c_uint64, dbl, dbl, dbl, dbl],
+            "cpic_enable_push_stats": [vp, i32],
+            "cpic_push_stats_get": [vp, C.POINTER(PushStats)],
+            "cpic_device_ptr": [vp, C.c_int, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)],
+            "cpic_set_stream": [vp, vp],
+            "cpic_set_num_particles": [vp, i64],
+            "cpic_set_modes": [vp, i32, i32],
+            "cpic_last_ms": [vp, C.c_int, C.POINTER(dbl)],
+            "cpic_launch_count": [vp, C.POINTER(i64)],
+        }
+        for name, args in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy", "cpic_sync", "cpic_num_cells",
+            "cpic_num_particles", "cpic_upload_particles", "cpic_download_particles", "cpic_upload_fields",
+            "cpic_download_fields", "cpic_upload_interpolators", "cpic_download_interpolators",
+            "cpic_upload_accumulators", "cpic_download_accumulators", "cpic_load_interpolator_array",
+            "cpic_initialize_interpolator", "cpic_clear_accumulator_array", "cpic_push", "cpic_contribute",
+            "cpic_unload_accumulator_array", "cpic_advance_b", "cpic_advance_e", "cpic_uncenter_particles",
+            "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_sort_particles", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
+            "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
+            "cpic_last_ms", "cpic_launch_count"]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One simulation context on one GPU (thin wrapper over ``cpic_ctx``).
+
+    Method names follow the reference's call surface (example/example.cpp:221-266).
+    All arrays are host numpy arrays; ``real`` is float32 or float64.
+    """
+
+    def __init__(self, nx, ny, nz, ng=1, max_particles=0, real=np.float32, solver=SOLVER_EM,
+                 boundary=BOUNDARY_PERIODIC, device=0, fp_mode=FP_STRICT, deposit_mode=DEPOSIT_AUTO,
+                 enable_sort=True):
+        self.L = lib()
+        self.real = np.dtype(real)
+        self.params = Params(nx=nx, ny=ny, nz=nz, ng=ng, real_bytes=self.real.itemsize, solver=solver,
+                             boundary=boundary, device=device, fp_mode=fp_mode, deposit_mode=deposit_mode,
+                             max_particles=int(max_particles), enable_sort=1 if enable_sort else 0)
+        h = C.c_void_p()
+        rc = self.L.cpic_create(C.byref(self.params), C.byref(h))
+        if rc != 0:
+            raise CpicError(rc, (self.L.cpic_last_error(None) or b"").decode())
+        self.h = h
+        self.nx, self.ny, self.nz, self.ng = nx, ny, nz, ng
+        self.nc = (nx + 2 * ng) * (ny + 2 * ng) * (nz + 2 * ng)
+        self.solver = solver
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cpic_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CpicError(rc, (self.L.cpic_last_error(self.h) or b"").decode())
+
+    # ---- transfers ------------------------------------------------------------------
+    @property
+    def num_particles(self):
+        n = C.c_int64()
+        self._ck(self.L.cpic_num_particles(self.h, C.byref(n)))
+        return n.value
+
+    def upload_particles(self, p: dict):
+        n = len(p["cell"])
+        arrs = [np.ascontiguousarray(p[k], dtype=self.real) for k in PARTICLE_NAMES[:7]]
+        cell = np.ascontiguousarray(p["cell"], dtype=np.int32)
+        self._ck(self.L.cpic_upload_particles(self.h, *[_p(a) for a in arrs], _p(cell), n))
+
+    def download_particles(self) -> dict:
+        n = self.num_particles
+        out = {k: np.empty(n, dtype=self.real) for k in PARTICLE_NAMES[:7]}
+        out["cell"] = np.empty(n, dtype=np.int32)
+        got = C.c_int64()
+        self._ck(self.L.cpic_download_particles(self.h, *[_p(out[k]) for k in PARTICLE_NAMES], n, C.byref(got)))
+        return out
+
+    def upload_fields(self, f):
+        f = np.ascontiguousarray(f, dtype=self.real)
+        assert f.shape == (9, self.nc)
+        ptrs = (C.c_void_p * 9)(*[f[m].ctypes.data for m in range(9)])
+        self._ck(self.L.cpic_upload_fields(self.h, ptrs))
+
+    def download_fields(self):
+        f = np.empty((9, self.nc), dtype=self.real)
+        ptrs = (C.c_void_p * 9)(*[f[m].ctypes.data for m in range(9)])
+        self._ck(self.L.cpic_download_fields(self.h, ptrs))
+        return f
+
+    def upload_interpolators(self, a):
+        a = np.ascontiguousarray(a, dtype=self.real)
+        assert a.shape == (self.nc, 18)
+        self._ck(self.L.cpic_upload_interpolators(self.h, _p(a)))
+
+    def download_interpolators(self):
+        a = np.empty((self.nc, 18), dtype=self.real)
+        self._ck(self.L.cpic_download_interpolators(self.h, _p(a)))
+        return a
+
+    def upload_accumulators(self, a):
+        a = np.ascontiguousarray(a, dtype=self.real)
+        assert a.shape == (self.nc, 12)
+        self._ck(self.L.cpic_upload_accumulators(self.h, _p(a)))
+
+    def download_accumulators(self):
+        a = np.empty((self.nc, 12), dtype=self.real)
+        self._ck(self.L.cpic_download_accumulators(self.h, _p(a)))
+        return a
+
+    # ---- the time-loop call surface ---------------------------------------------------
+    def load_interpolator_array(self):
+        self._ck(self.L.cpic_load_interpolator_array(self.h))
+
+    def initialize_interpolator(self):
+        self._ck(self.L.cpic_initialize_interpolator(self.h))
+
+    def clear_accumulator_array(self):
+        self._ck(self.L.cpic_clear_accumulator_array(self.h))
+
+    def push(self, k: Consts):
+        self._ck(self.L.cpic_push(self.h, C.byref(k)))
+
+    def contribute(self):
+        self._ck(self.L.cpic_contribute(self.h))
+
+    def unload_accumulator_array(self, k: Consts):
+        self._ck(self.L.cpic_unload_accumulator_array(self.h, C.byref(k)))
+
+    def advance_b(self, px, py, pz):
+        self._ck(self.L.cpic_advance_b(self.h, px, py, pz))
+
+    def advance_e(self, px, py, pz, dt_eps0):
+        self._ck(self.L.cpic_advance_e(self.h, px, py, pz, dt_eps0))
+
+    def uncenter_particles(self, qdt_2mc):
+        self._ck(self.L.cpic_uncenter_particles(self.h, qdt_2mc))
+
+    def update_ghosts(self, which):
+        self._ck(self.L.cpic_update_ghosts(self.h, which))
+
+    def energies(self):
+        e, b = C.c_double(), C.c_double()
+        self._ck(self.L.cpic_energies(self.h, C.byref(e), C.byref(b)))
+        return e.value, b.value
+
+    def step(self, k: Consts, nsteps=1, sort_interval=0, energies=False):
+        en = np.zeros((nsteps, 2)) if energies else None
+        self._ck(self.L.cpic_step(self.h, C.byref(k), nsteps, sort_interval, _p(en)))
+        return en
+
+    def sort_particles(self):
+        self._ck(self.L.cpic_sort_particles(self.h))
+
+    def init_uniform_plasma(self, first, count, gnx, gny, gnz, nppc, z0=0, seed=12345, vth=(0.1, 0.1, 0.1),
+                            weight=1.0):
+        self._ck(self.L.cpic_init_uniform_plasma(self.h, first, count, gnx, gny, gnz, nppc, z0, seed,
+                                                 float(vth[0]), float(vth[1]), float(vth[2]), float(weight)))
+
+    def sync(self):
+        self._ck(self.L.cpic_sync(self.h))
+
+    # ---- diagnostics / interop ----------------------------------------------------------
+    def enable_push_stats(self, on=True):
+        self._ck(self.L.cpic_enable_push_stats(self.h, 1 if on else 0))
+
+    def push_stats(self):
+        s = PushStats()
+        self._ck(self.L.cpic_push_stats_get(self.h, C.byref(s)))
+        return {"movers": s.movers, "crossings": s.crossings, "wraps": list(s.wraps)}
+
+    def set_modes(self, fp_mode, deposit_mode):
+        self._ck(self.L.cpic_set_modes(self.h, fp_mode, deposit_mode))
+
+    def set_num_particles(self, n):
+        self._ck(self.L.cpic_set_num_particles(self.h, n))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.cpic_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def device_ptr(self, which):
+        p, n, s = C.c_void_p(), C.c_int64(), C.c_int64()
+        self._ck(self.L.cpic_device_ptr(self.h, which, C.byref(p), C.byref(n), C.byref(s)))
+        return p.value, n.value, s.value
+
+    def last_ms(self, what):
+        ms = C.c_double()
+        self._ck(self.L.cpic_last_ms(self.h, what, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launch_count(self):
+        n = C.c_int64()
+        self._ck(self.L.cpic_launch_count(self.h, C.byref(n)))
+        return n.value

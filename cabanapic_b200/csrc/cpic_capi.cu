@@ -1,0 +1,635 @@
+// C ABI of cabanapic_b200 (include/cabanapic_b200.h): context, device memory, launch logic.
+// Host side is plain C++; all compute is in the hand-written sm_100a kernels included below.
+// There is deliberately no CPU fallback anywhere in this file.
+#include "../../include/cabanapic_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "cpic_common.cuh"
+#include "cpic_fields.cuh"
+#include "cpic_particles.cuh"
+#include "cpic_sort.cuh"
+#include "cpic_init.cuh"
+
+using namespace cpic;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CtxBase {
+    cpic_params prm{};
+    Grid g{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    long long np = 0;
+    long long launches = 0;
+    cudaEvent_t ev[8]{};   // 0/1 push, 2/3 sort, 4/5 field side, 6/7 step
+    bool ev_valid[4] = {false, false, false, false};
+    bool want_stats = false;
+    virtual ~CtxBase() {}
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int cuda(cudaError_t e, const char* what) {
+        if (e == cudaSuccess) return CPIC_OK;
+        return fail(e == cudaErrorMemoryAllocation ? CPIC_E_NOMEM : CPIC_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    int check_launch(const char* what) {
+        ++launches;
+        return cuda(cudaGetLastError(), what);
+    }
+
+    virtual int upload_particles(const void* const m[7], const int32_t* cell, long long n) = 0;
+    virtual int download_particles(void* const m[7], int32_t* cell, long long cap, long long* n_out) = 0;
+    virtual int upload_fields(const void* const f[9]) = 0;
+    virtual int download_fields(void* const f[9]) = 0;
+    virtual int xfer_interp(void* host, bool up) = 0;
+    virtual int xfer_acc(void* host, bool up) = 0;
+    virtual int load_interpolator() = 0;
+    virtual int initialize_interpolator() = 0;
+    virtual int clear_accumulator() = 0;
+    virtual int push(const cpic_consts& k) = 0;
+    virtual int unload_accumulator(const cpic_consts& k) = 0;
+    virtual int advance_b(double px, double py, double pz) = 0;
+    virtual int advance_e(double px, double py, double pz, double dt_eps0) = 0;
+    virtual int uncenter(double qdt_2mc) = 0;
+    virtual int energies_async(double* dev_out2) = 0;
+    virtual int update_ghosts(int which) = 0;
+    virtual int sort() = 0;
+    virtual int init_uniform(const UniformPlasmaArgs& a) = 0;
+    virtual int device_ptr(int which, void** ptr, int64_t* count, int64_t* stride) = 0;
+    virtual double* energy_scratch() = 0;
+    virtual unsigned long long* stats_dev() = 0;
+};
+
+inline unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
+
+template <class R>
+struct Ctx final : CtxBase {
+    static constexpr int S = IpStride<R>::value;
+    long long nc_pad = 0;
+    // particle store: two buffers (second only with enable_sort), members padded to 16 B multiples
+    long long cap = 0;
+    char* pbuf[2] = {nullptr, nullptr};
+    Particles<R> P[2];
+    int cur = 0;
+    R* fields = nullptr;       // 9 * nc_pad
+    R* interp = nullptr;       // nc * S
+    R* acc = nullptr;          // nc * 12
+    unsigned* cell_count = nullptr;   // nc (+ scan scratch)
+    unsigned* scan_l1 = nullptr;
+    unsigned* scan_l2 = nullptr;
+    long long n_l1 = 0, n_l2 = 0;
+    unsigned* bad = nullptr;
+    double* en_dev = nullptr;          // 2 doubles scratch
+    unsigned long long* stats = nullptr;  // 8 counters
+
+    ~Ctx() override {
+        if (stream || true) {
+            cudaSetDevice(prm.device);
+            for (auto& e : ev) if (e) cudaEventDestroy(e);
+            cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(fields); cudaFree(interp); cudaFree(acc);
+            cudaFree(cell_count); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats);
+            if (own_stream && stream) cudaStreamDestroy(stream);
+        }
+    }
+
+    Fields<R> F() const {
+        Fields<R> f;
+        for (int m = 0; m < F_N; ++m) f.c[m] = fields + (long long)m * nc_pad;
+        return f;
+    }
+
+    void carve(int b) {
+        char* p = pbuf[b];
+        const long long stride_r = cap * (long long)sizeof(R), stride_i = cap * (long long)sizeof(int);
+        P[b].dx = (R*)p; p += stride_r; P[b].dy = (R*)p; p += stride_r; P[b].dz = (R*)p; p += stride_r;
+        P[b].ux = (R*)p; p += stride_r; P[b].uy = (R*)p; p += stride_r; P[b].uz = (R*)p; p += stride_r;
+        P[b].w = (R*)p; p += stride_r; P[b].cell = (int*)p; p += stride_i;
+    }
+
+    int init() {
+        int rc;
+        if ((rc = cuda(cudaSetDevice(prm.device), "cudaSetDevice"))) return rc;
+        if ((rc = cuda(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return rc;
+        own_stream = true;
+        for (auto& e : ev)
+            if ((rc = cuda(cudaEventCreate(&e), "cudaEventCreate"))) return rc;
+        nc_pad = (g.nc + 63) / 64 * 64;
+        cap = (prm.max_particles + 63) / 64 * 64;
+        if (cap < 64) cap = 64;
+        const size_t pbytes = (size_t)cap * (7 * sizeof(R) + sizeof(int));
+        for (int b = 0; b < (prm.enable_sort ? 2 : 1); ++b) {
+            if ((rc = cuda(cudaMalloc(&pbuf[b], pbytes), "cudaMalloc(particles)"))) return rc;
+            carve(b);
+        }
+        if ((rc = cuda(cudaMalloc(&fields, (size_t)nc_pad * F_N * sizeof(R)), "cudaMalloc(fields)"))) return rc;
+        if ((rc = cuda(cudaMalloc(&interp, (size_t)g.nc * S * sizeof(R)), "cudaMalloc(interpolators)"))) return rc;
+        if ((rc = cuda(cudaMalloc(&acc, (size_t)g.nc * 12 * sizeof(R)), "cudaMalloc(accumulators)"))) return rc;
+        if ((rc = cuda(cudaMalloc(&bad, sizeof(unsigned)), "cudaMalloc"))) return rc;
+        if ((rc = cuda(cudaMalloc(&en_dev, 2 * sizeof(double)), "cudaMalloc"))) return rc;
+        if ((rc = cuda(cudaMalloc(&stats, 8 * sizeof(unsigned long long)), "cudaMalloc"))) return rc;
+        if (prm.enable_sort) {
+            n_l1 = (g.nc + SCAN_TILE - 1) / SCAN_TILE;
+            n_l2 = (n_l1 + SCAN_TILE - 1) / SCAN_TILE;
+            if (n_l2 > SCAN_TILE) return fail(CPIC_E_INVALID, "grid too large for the 3-level cell scan");
+            if ((rc = cuda(cudaMalloc(&cell_count, (size_t)g.nc * sizeof(unsigned)), "cudaMalloc(cell_count)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&scan_l1, (size_t)n_l1 * sizeof(unsigned)), "cudaMalloc"))) return rc;
+            if ((rc = cuda(cudaMalloc(&scan_l2, (size_t)n_l2 * sizeof(unsigned)), "cudaMalloc"))) return rc;
+        }
+        // Field_Solver ctor zeroes the fields (src/fields.h:279-315); interpolators are zeroed by
+        // initialize_interpolator (src/interpolator.cpp:125-172); Kokkos::View zero-initialises.
+        cudaMemsetAsync(fields, 0, (size_t)nc_pad * F_N * sizeof(R), stream);
+        cudaMemsetAsync(interp, 0, (size_t)g.nc * S * sizeof(R), stream);
+        cudaMemsetAsync(acc, 0, (size_t)g.nc * 12 * sizeof(R), stream);
+        cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
+        return cuda(cudaStreamSynchronize(stream), "init");
+    }
+
+    // ------------------------------------------------------------------ transfers
+    int upload_particles(const void* const m[7], const int32_t* cell, long long n) override {
+        if (n < 0 || n > cap) return fail(CPIC_E_CAPACITY, "upload_particles: %lld particles exceed capacity %lld", n, cap);
+        Particles<R>& p = P[cur];
+        R* dst[7] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w};
+        int rc;
+        for (int k = 0; k < 7; ++k)
+            if ((rc = cuda(cudaMemcpyAsync(dst[k], m[k], (size_t)n * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D particles"))) return rc;
+        if ((rc = cuda(cudaMemcpyAsync(p.cell, cell, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream), "H2D cell"))) return rc;
+        np = n;
+        // bounds-check the cell indices once on upload (would have caught decks/2stream-short.cxx)
+        cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
+        if (n > 0) {
+            k_check_cells<<<blocks_for(n), 256, 0, stream>>>(p.cell, n, g.nc, bad);
+            if ((rc = check_launch("k_check_cells"))) return rc;
+        }
+        unsigned nbad = 0;
+        if ((rc = cuda(cudaMemcpyAsync(&nbad, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(stream), "upload_particles"))) return rc;
+        if (nbad) { np = 0; return fail(CPIC_E_BAD_CELL, "upload_particles: %u particles have a cell index outside [0,%lld)", nbad, g.nc); }
+        return CPIC_OK;
+    }
+    int download_particles(void* const m[7], int32_t* cell, long long capacity, long long* n_out) override {
+        if (capacity < np) return fail(CPIC_E_CAPACITY, "download_particles: buffer holds %lld, need %lld", capacity, np);
+        Particles<R>& p = P[cur];
+        R* src[7] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w};
+        int rc;
+        for (int k = 0; k < 7; ++k)
+            if (m[k] && (rc = cuda(cudaMemcpyAsync(m[k], src[k], (size_t)np * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H particles"))) return rc;
+        if (cell && (rc = cuda(cudaMemcpyAsync(cell, p.cell, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H cell"))) return rc;
+        if (n_out) *n_out = np;
+        return cuda(cudaStreamSynchronize(stream), "download_particles");
+    }
+    int upload_fields(const void* const f[9]) override {
+        int rc;
+        for (int m = 0; m < F_N; ++m)
+            if ((rc = cuda(cudaMemcpyAsync(fields + (long long)m * nc_pad, f[m], (size_t)g.nc * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D fields"))) return rc;
+        return cuda(cudaStreamSynchronize(stream), "upload_fields");
+    }
+    int download_fields(void* const f[9]) override {
+        int rc;
+        for (int m = 0; m < F_N; ++m)
+            if (f[m] && (rc = cuda(cudaMemcpyAsync(f[m], fields + (long long)m * nc_pad, (size_t)g.nc * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H fields"))) return rc;
+        return cuda(cudaStreamSynchronize(stream), "download_fields");
+    }
+    int xfer_interp(void* host, bool up) override {
+        // host layout [nc][18]; device records are padded to S reals
+        int rc;
+        if (up)
+            rc = cuda(cudaMemcpy2DAsync(interp, S * sizeof(R), host, 18 * sizeof(R), 18 * sizeof(R), (size_t)g.nc, cudaMemcpyHostToDevice, stream), "H2D interpolators");
+        else
+            rc = cuda(cudaMemcpy2DAsync(host, 18 * sizeof(R), interp, S * sizeof(R), 18 * sizeof(R), (size_t)g.nc, cudaMemcpyDeviceToHost, stream), "D2H interpolators");
+        if (rc) return rc;
+        return cuda(cudaStreamSynchronize(stream), "xfer_interp");
+    }
+    int xfer_acc(void* host, bool up) override {
+        int rc = up ? cuda(cudaMemcpyAsync(acc, host, (size_t)g.nc * 12 * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D accumulators")
+                    : cuda(cudaMemcpyAsync(host, acc, (size_t)g.nc * 12 * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H accumulators");
+        if (rc) return rc;
+        return cuda(cudaStreamSynchronize(stream), "xfer_acc");
+    }
+
+    // ------------------------------------------------------------------ field side
+    int load_interpolator() override {
+        Box b{g.ng, g.ng, g.ng, g.nx, g.ny, g.nz};
+        k_load_interpolator<R><<<blocks_for(b.count()), 256, 0, stream>>>(F(), interp, g, b);
+        return check_launch("k_load_interpolator");
+    }
+    int initialize_interpolator() override {
+        return cuda(cudaMemsetAsync(interp, 0, (size_t)g.nc * S * sizeof(R), stream), "initialize_interpolator");
+    }
+    int clear_accumulator() override {
+        return cuda(cudaMemsetAsync(acc, 0, (size_t)g.nc * 12 * sizeof(R), stream), "clear_accumulator");
+    }
+    int unload_accumulator(const cpic_consts& k) override {
+        // src/accumulator.cpp:66-68: products in real_t, 0.25/x in double, narrowed to real_t
+        const R dx = (R)k.dx, dy = (R)k.dy, dz = (R)k.dz, dt = (R)k.dt;
+        const R cx = (R)(0.25 / (double)(R)(dy * dz * dt));
+        const R cy = (R)(0.25 / (double)(R)(dz * dx * dt));
+        const R cz = (R)(0.25 / (double)(R)(dx * dy * dt));
+        Box b{g.ng, g.ng, g.ng, g.nx + 1, g.ny + 1, g.nz + 1};
+        k_unload_accumulator<R><<<blocks_for(b.count()), 256, 0, stream>>>(F(), acc, g, b, cx, cy, cz);
+        return check_launch("k_unload_accumulator");
+    }
+    int ghost_copy(int m0) {
+        Fields<R> f = F();
+        k_ghost_copy3<R><<<blocks_for(g.nc), 256, 0, stream>>>(f.c[m0], f.c[m0 + 1], f.c[m0 + 2], g);
+        return check_launch("k_ghost_copy3");
+    }
+    int ghost_fold() {
+        Fields<R> f = F();
+        const long long m0 = std::max({(long long)g.nx * (g.nz + 1), (long long)g.ny * (g.nx + 1), (long long)g.nz * (g.ny + 1)});
+        const long long m1 = std::max({(long long)g.nx * (g.ny + 1), (long long)g.ny * (g.nz + 1), (long long)g.nz * (g.nx + 1)});
+        k_ghost_fold<R, 0><<<dim3(blocks_for(m0), 3), 256, 0, stream>>>(f.c[F_JFX], f.c[F_JFY], f.c[F_JFZ], g);
+        int rc = check_launch("k_ghost_fold<0>");
+        if (rc) return rc;
+        k_ghost_fold<R, 1><<<dim3(blocks_for(m1), 3), 256, 0, stream>>>(f.c[F_JFX], f.c[F_JFY], f.c[F_JFZ], g);
+        return check_launch("k_ghost_fold<1>");
+    }
+    int update_ghosts(int which) override {
+        if (which == 0) return ghost_fold();
+        if (which == 1) return ghost_copy(F_JFX);
+        if (which == 2) return ghost_copy(F_CBX);
+        return fail(CPIC_E_INVALID, "update_ghosts: which=%d", which);
+    }
+    int advance_b(double px, double py, double pz) override {
+        if (prm.solver == CPIC_SOLVER_ES_1D) return CPIC_OK;  // src/fields.h:470-482: no-op
+        Box b{1, 1, 1, g.nx, g.ny, g.nz};
+        k_advance_b<R><<<blocks_for(b.count()), 256, 0, stream>>>(F(), g, b, (R)px, (R)py, (R)pz);
+        int rc = check_launch("k_advance_b");
+        if (rc) return rc;
+        return ghost_copy(F_CBX);   // src/fields.h:718
+    }
+    int advance_e(double px, double py, double pz, double dt_eps0) override {
+        int rc = ghost_fold();                                   // src/fields.h:642 / :530
+        if (rc) return rc;
+        if (prm.solver == CPIC_SOLVER_ES_1D) {
+            k_advance_e_es<R><<<blocks_for(g.nc), 256, 0, stream>>>(F(), g.nc, (R)dt_eps0);
+            return check_launch("k_advance_e_es");
+        }
+        if ((rc = ghost_copy(F_JFX))) return rc;                 // src/fields.h:643
+        Box b{1, 1, 1, g.nx + 1, g.ny + 1, g.nz + 1};
+        k_advance_e_em<R><<<blocks_for(b.count()), 256, 0, stream>>>(F(), g, b, (R)px, (R)py, (R)pz, (R)dt_eps0);
+        return check_launch("k_advance_e_em");
+    }
+    int energies_async(double* dev_out2) override {
+        cudaMemsetAsync(dev_out2, 0, 2 * sizeof(double), stream);
+        const bool em = prm.solver == CPIC_SOLVER_EM;
+        Box b = em ? Box{1, 1, 1, g.nx, g.ny, g.nz} : Box{0, 0, 0, g.gx, g.gy, g.gz};
+        unsigned nb = blocks_for(b.count());
+        if (nb > 148 * 8) nb = 148 * 8;
+        k_energy<R><<<nb, 256, 0, stream>>>(F(), g, b, em ? 1 : 0, dev_out2);
+        return check_launch("k_energy");
+    }
+    double* energy_scratch() override { return en_dev; }
+    unsigned long long* stats_dev() override { return stats; }
+
+    // ------------------------------------------------------------------ particles
+    template <bool FMA, int DEP>
+    int launch_push(const PushArgs<R>& a) {
+        if (want_stats) k_push<R, FMA, DEP, true><<<blocks_for(np), 256, 0, stream>>>(a);
+        else k_push<R, FMA, DEP, false><<<blocks_for(np), 256, 0, stream>>>(a);
+        return check_launch("k_push");
+    }
+    int push(const cpic_consts& k) override {
+        if (np == 0) return CPIC_OK;
+        PushArgs<R> a;
+        a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
+        a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
+        a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.ng = g.ng; a.gx = g.gx; a.gy = g.gy;
+        a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC;
+        a.stats = stats;
+        if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
+        cudaEventRecord(ev[0], stream);
+        int dep = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
+        const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
+        int rc;
+        if (dep == CPIC_DEPOSIT_ATOMIC) rc = fma ? launch_push<true, 1>(a) : launch_push<false, 1>(a);
+        else if (dep == CPIC_DEPOSIT_ATOMIC_V4) rc = fma ? launch_push<true, 2>(a) : launch_push<false, 2>(a);
+        else rc = fma ? launch_push<true, 3>(a) : launch_push<false, 3>(a);
+        cudaEventRecord(ev[1], stream);
+        ev_valid[0] = true;
+        return rc;
+    }
+    int uncenter(double qdt_2mc) override {
+        if (np == 0) return CPIC_OK;
+        if (prm.fp_mode == CPIC_FP_CONTRACT) k_uncenter<R, true><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, interp, (R)qdt_2mc);
+        else k_uncenter<R, false><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, interp, (R)qdt_2mc);
+        return check_launch("k_uncenter");
+    }
+
+    int scan_cells() {
+        // exclusive scan of cell_count in place (3 levels of 2048-wide tiles)
+        k_scan_tile<<<(unsigned)n_l1, 256, 0, stream>>>(cell_count, cell_count, g.nc, scan_l1);
+        int rc = check_launch("k_scan_tile");
+        if (rc) return rc;
+        if (n_l1 > 1) {
+            k_scan_tile<<<(unsigned)n_l2, 256, 0, stream>>>(scan_l1, scan_l1, n_l1, scan_l2);
+            if ((rc = check_launch("k_scan_tile"))) return rc;
+            if (n_l2 > 1) {
+                k_scan_tile<<<1, 256, 0, stream>>>(scan_l2, scan_l2, n_l2, nullptr);
+                if ((rc = check_launch("k_scan_tile"))) return rc;
+                k_scan_add<<<(unsigned)n_l2, 256, 0, stream>>>(scan_l1, n_l1, scan_l2);
+                if ((rc = check_launch("k_scan_add"))) return rc;
+            }
+            k_scan_add<<<(unsigned)n_l1, 256, 0, stream>>>(cell_count, g.nc, scan_l1);
+            if ((rc = check_launch("k_scan_add"))) return rc;
+        }
+        return CPIC_OK;
+    }
+    int sort() override {
+        if (!prm.enable_sort) return fail(CPIC_E_INVALID, "sort_particles: context was created with enable_sort=0");
+        if (np == 0) return CPIC_OK;
+        int rc;
+        cudaEventRecord(ev[2], stream);
+        cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
+        cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
+        k_cell_histogram<<<blocks_for(np), 256, 0, stream>>>(P[cur].cell, np, g.nc, cell_count, bad);
+        if ((rc = check_launch("k_cell_histogram"))) return rc;
+        if ((rc = scan_cells())) return rc;
+        k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
+        if ((rc = check_launch("k_sort_scatter"))) return rc;
+        cur ^= 1;
+        cudaEventRecord(ev[3], stream);
+        ev_valid[1] = true;
+        return CPIC_OK;
+    }
+
+    int init_uniform(const UniformPlasmaArgs& a) override {
+        if (a.count < 0 || a.count > cap) return fail(CPIC_E_CAPACITY, "init_uniform_plasma: %lld particles exceed capacity %lld", a.count, cap);
+        if (a.gnx != g.nx || a.gny != g.ny) return fail(CPIC_E_INVALID, "init_uniform_plasma: x/y extents must equal the context's");
+        np = a.count;
+        if (np == 0) return CPIC_OK;
+        k_init_uniform_plasma<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], a);
+        return check_launch("k_init_uniform_plasma");
+    }
+
+    int device_ptr(int which, void** ptr, int64_t* count, int64_t* stride) override {
+        Particles<R>& p = P[cur];
+        void* pm[8] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w, p.cell};
+        if (which >= 0 && which < 8) { *ptr = pm[which]; if (count) *count = cap; if (stride) *stride = 1; return CPIC_OK; }
+        if (which == 16) { *ptr = fields; if (count) *count = g.nc; if (stride) *stride = nc_pad; return CPIC_OK; }
+        if (which == 17) { *ptr = interp; if (count) *count = g.nc; if (stride) *stride = S; return CPIC_OK; }
+        if (which == 18) { *ptr = acc; if (count) *count = g.nc; if (stride) *stride = 12; return CPIC_OK; }
+        return fail(CPIC_E_INVALID, "device_ptr: which=%d", which);
+    }
+};
+
+int validate(const cpic_params& p, std::string& why) {
+    char buf[256];
+    if (p.nx < 1 || p.ny < 1 || p.nz < 1) { why = "nx, ny, nz must be >= 1"; return CPIC_E_INVALID; }
+    if (p.ng != 1) { why = "ng must be 1 (the reference's mover hard-wires one ghost layer, src/move_p.h:19-47)"; return CPIC_E_INVALID; }
+    if (p.real_bytes != 4 && p.real_bytes != 8) { why = "real_bytes must be 4 or 8"; return CPIC_E_INVALID; }
+    if (p.solver != CPIC_SOLVER_EM && p.solver != CPIC_SOLVER_ES_1D) { why = "unknown solver"; return CPIC_E_INVALID; }
+    if (p.solver == CPIC_SOLVER_ES_1D && (p.ny > 1 || p.nz > 1)) { why = "ES field solver supports 1D only (example/example.cpp:69-74)"; return CPIC_E_INVALID; }
+    if (p.boundary == CPIC_BOUNDARY_REFLECT) { why = "Boundary::Reflect is not implemented (the reference exits, src/fields.h:21-25,113-117)"; return CPIC_E_UNSUPPORTED; }
+    if (p.boundary != CPIC_BOUNDARY_PERIODIC) { why = "unknown boundary"; return CPIC_E_INVALID; }
+    if (p.max_particles < 0 || p.max_particles > (1ll << 31) - 64) { why = "max_particles must be in [0, 2^31)"; return CPIC_E_INVALID; }
+    const long long nc = (long long)(p.nx + 2) * (p.ny + 2) * (p.nz + 2);
+    if (nc > (1ll << 31) - 1) { snprintf(buf, sizeof buf, "%lld cells overflow the int cell index", nc); why = buf; return CPIC_E_INVALID; }
+    if (p.fp_mode != CPIC_FP_STRICT && p.fp_mode != CPIC_FP_CONTRACT) { why = "unknown fp_mode"; return CPIC_E_INVALID; }
+    if (p.deposit_mode < 0 || p.deposit_mode > 3) { why = "unknown deposit_mode"; return CPIC_E_INVALID; }
+    return CPIC_OK;
+}
+
+#define CTX_OR_FAIL(ctx) \
+    if (!(ctx)) return CPIC_E_INVALID; \
+    CtxBase* c = reinterpret_cast<CtxBase*>(ctx); \
+    { cudaError_t e_ = cudaSetDevice(c->prm.device); if (e_ != cudaSuccess) return c->cuda(e_, "cudaSetDevice"); }
+
+}  // namespace
+
+extern "C" {
+
+int cpic_abi_version(void) { return CPIC_ABI_VERSION; }
+
+const char* cpic_last_error(const cpic_ctx* ctx) {
+    if (!ctx) return g_create_error.c_str();
+    return reinterpret_cast<const CtxBase*>(ctx)->err.c_str();
+}
+
+int cpic_create(const cpic_params* params, cpic_ctx** out) {
+    if (!params || !out) { g_create_error = "cpic_create: null argument"; return CPIC_E_INVALID; }
+    *out = nullptr;
+    int rc = validate(*params, g_create_error);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return CPIC_E_CUDA;
+    }
+    if (params->device < 0 || params->device >= ndev) { g_create_error = "device ordinal out of range"; return CPIC_E_INVALID; }
+    CtxBase* c = (params->real_bytes == 4) ? static_cast<CtxBase*>(new Ctx<float>()) : static_cast<CtxBase*>(new Ctx<double>());
+    c->prm = *params;
+    c->g = make_grid(params->nx, params->ny, params->nz, params->ng);
+    rc = (params->real_bytes == 4) ? static_cast<Ctx<float>*>(c)->init() : static_cast<Ctx<double>*>(c)->init();
+    if (rc) { g_create_error = c->err; delete c; return rc; }
+    *out = reinterpret_cast<cpic_ctx*>(c);
+    return CPIC_OK;
+}
+
+void cpic_destroy(cpic_ctx* ctx) {
+    if (!ctx) return;
+    CtxBase* c = reinterpret_cast<CtxBase*>(ctx);
+    cudaSetDevice(c->prm.device);
+    cudaStreamSynchronize(c->stream);
+    delete c;
+}
+
+int cpic_sync(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->cuda(cudaStreamSynchronize(c->stream), "sync"); }
+int cpic_num_cells(const cpic_ctx* ctx, int64_t* out) { if (!ctx || !out) return CPIC_E_INVALID; *out = reinterpret_cast<const CtxBase*>(ctx)->g.nc; return CPIC_OK; }
+int cpic_num_particles(const cpic_ctx* ctx, int64_t* out) { if (!ctx || !out) return CPIC_E_INVALID; *out = reinterpret_cast<const CtxBase*>(ctx)->np; return CPIC_OK; }
+
+int cpic_upload_particles(cpic_ctx* ctx, const void* dx, const void* dy, const void* dz, const void* ux, const void* uy,
+                          const void* uz, const void* w, const int32_t* cell, int64_t n) {
+    CTX_OR_FAIL(ctx);
+    if (n > 0 && (!dx || !dy || !dz || !ux || !uy || !uz || !w || !cell)) return c->fail(CPIC_E_INVALID, "upload_particles: null member array");
+    const void* m[7] = {dx, dy, dz, ux, uy, uz, w};
+    return c->upload_particles(m, cell, n);
+}
+int cpic_download_particles(cpic_ctx* ctx, void* dx, void* dy, void* dz, void* ux, void* uy, void* uz, void* w,
+                            int32_t* cell, int64_t capacity, int64_t* n_out) {
+    CTX_OR_FAIL(ctx);
+    void* m[7] = {dx, dy, dz, ux, uy, uz, w};
+    long long n = 0;
+    int rc = c->download_particles(m, cell, capacity, &n);
+    if (n_out) *n_out = n;
+    return rc;
+}
+int cpic_upload_fields(cpic_ctx* ctx, const void* const fields[9]) {
+    CTX_OR_FAIL(ctx);
+    for (int m = 0; m < 9; ++m) if (!fields || !fields[m]) return c->fail(CPIC_E_INVALID, "upload_fields: null member %d", m);
+    return c->upload_fields(fields);
+}
+int cpic_download_fields(cpic_ctx* ctx, void* const fields[9]) { CTX_OR_FAIL(ctx); if (!fields) return c->fail(CPIC_E_INVALID, "download_fields: null"); return c->download_fields(fields); }
+int cpic_upload_interpolators(cpic_ctx* ctx, const void* interp) { CTX_OR_FAIL(ctx); if (!interp) return c->fail(CPIC_E_INVALID, "null"); return c->xfer_interp(const_cast<void*>(interp), true); }
+int cpic_download_interpolators(cpic_ctx* ctx, void* interp) { CTX_OR_FAIL(ctx); if (!interp) return c->fail(CPIC_E_INVALID, "null"); return c->xfer_interp(interp, false); }
+int cpic_upload_accumulators(cpic_ctx* ctx, const void* acc) { CTX_OR_FAIL(ctx); if (!acc) return c->fail(CPIC_E_INVALID, "null"); return c->xfer_acc(const_cast<void*>(acc), true); }
+int cpic_download_accumulators(cpic_ctx* ctx, void* acc) { CTX_OR_FAIL(ctx); if (!acc) return c->fail(CPIC_E_INVALID, "null"); return c->xfer_acc(acc, false); }
+
+int cpic_load_interpolator_array(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->load_interpolator(); }
+int cpic_initialize_interpolator(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->initialize_interpolator(); }
+int cpic_clear_accumulator_array(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->clear_accumulator(); }
+int cpic_push(cpic_ctx* ctx, const cpic_consts* k) { CTX_OR_FAIL(ctx); if (!k) return c->fail(CPIC_E_INVALID, "push: null consts"); return c->push(*k); }
+int cpic_contribute(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return CPIC_OK; }
+int cpic_unload_accumulator_array(cpic_ctx* ctx, const cpic_consts* k) { CTX_OR_FAIL(ctx); if (!k) return c->fail(CPIC_E_INVALID, "unload: null consts"); return c->unload_accumulator(*k); }
+int cpic_advance_b(cpic_ctx* ctx, double px, double py, double pz) { CTX_OR_FAIL(ctx); return c->advance_b(px, py, pz); }
+int cpic_advance_e(cpic_ctx* ctx, double px, double py, double pz, double dt_eps0) { CTX_OR_FAIL(ctx); return c->advance_e(px, py, pz, dt_eps0); }
+int cpic_uncenter_particles(cpic_ctx* ctx, double qdt_2mc) { CTX_OR_FAIL(ctx); return c->uncenter(qdt_2mc); }
+int cpic_update_ghosts(cpic_ctx* ctx, int which) { CTX_OR_FAIL(ctx); return c->update_ghosts(which); }
+int cpic_sort_particles(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->sort(); }
+
+int cpic_init_uniform_plasma(cpic_ctx* ctx, int64_t first, int64_t count, int32_t gnx, int32_t gny, int32_t gnz,
+                             int32_t nppc, int32_t z0, uint64_t seed, double vthx, double vthy, double vthz,
+                             double weight) {
+    CTX_OR_FAIL(ctx);
+    if (nppc < 1 || gnx < 1 || gny < 1 || gnz < 1 || first < 0) return c->fail(CPIC_E_INVALID, "init_uniform_plasma: bad arguments");
+    const long long total = (long long)gnx * gny * gnz * nppc;
+    if (first + count > total) return c->fail(CPIC_E_INVALID, "init_uniform_plasma: slice exceeds the global particle list");
+    // the slice must lie inside this context's z range [z0, z0+nz)
+    const long long per_plane = (long long)gnx * gny * nppc;
+    if (count > 0 && (first / per_plane < z0 || (first + count - 1) / per_plane >= (long long)z0 + c->g.nz))
+        return c->fail(CPIC_E_INVALID, "init_uniform_plasma: slice lies outside this context's z-planes");
+    UniformPlasmaArgs a;
+    a.first = first; a.count = count; a.gnx = gnx; a.gny = gny; a.gnz = gnz; a.nppc = nppc; a.z0 = z0;
+    a.lnx = c->g.nx; a.lny = c->g.ny; a.seed = seed; a.vth[0] = vthx; a.vth[1] = vthy; a.vth[2] = vthz; a.weight = weight;
+    return c->init_uniform(a);
+}
+
+int cpic_energies(cpic_ctx* ctx, double* e_energy, double* b_energy) {
+    CTX_OR_FAIL(ctx);
+    double* d = c->energy_scratch();
+    int rc = c->energies_async(d);
+    if (rc) return rc;
+    double h[2] = {0, 0};
+    if ((rc = c->cuda(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream), "D2H energies"))) return rc;
+    if ((rc = c->cuda(cudaStreamSynchronize(c->stream), "energies"))) return rc;
+    // reference: e_tot*0.5f*dV with dV = 1 (src/fields.h:584-585); B energy is 0 for ES
+    if (e_energy) *e_energy = 0.5 * h[0];
+    if (b_energy) *b_energy = (c->prm.solver == CPIC_SOLVER_EM) ? 0.5 * h[1] : 0.0;
+    return CPIC_OK;
+}
+
+int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, double* energies) {
+    CTX_OR_FAIL(ctx);
+    if (!k || nsteps < 0) return c->fail(CPIC_E_INVALID, "step: bad arguments");
+    int rc = CPIC_OK;
+    double* en = nullptr;
+    if (energies && nsteps > 0)
+        if ((rc = c->cuda(cudaMalloc(&en, (size_t)nsteps * 2 * sizeof(double)), "cudaMalloc(energies)"))) return rc;
+    cudaEventRecord(c->ev[6], c->stream);
+    const double hx = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->px) : 0.5 * k->px;
+    const double hy = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->py) : 0.5 * k->py;
+    const double hz = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->pz) : 0.5 * k->pz;
+    for (int64_t s = 0; s < nsteps && !rc; ++s) {
+        // example/example.cpp:221-266, plus the optional sort of :224-228
+        if (sort_interval > 0 && s % sort_interval == 0) rc = c->sort();
+        if (!rc) rc = c->load_interpolator();
+        if (!rc) rc = c->clear_accumulator();
+        if (!rc) rc = c->push(*k);
+        if (!rc) rc = c->unload_accumulator(*k);
+        if (!rc) rc = c->advance_b(hx, hy, hz);
+        if (!rc) rc = c->advance_e(k->px, k->py, k->pz, k->dt_eps0);
+        if (!rc) rc = c->advance_b(hx, hy, hz);
+        if (!rc && en) rc = c->energies_async(en + 2 * s);
+    }
+    cudaEventRecord(c->ev[7], c->stream);
+    c->ev_valid[3] = true;
+    if (!rc && en) {
+        rc = c->cuda(cudaMemcpyAsync(energies, en, (size_t)nsteps * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream), "D2H energies");
+        if (!rc) rc = c->cuda(cudaStreamSynchronize(c->stream), "step");
+        for (int64_t s = 0; s < nsteps && !rc; ++s) {
+            energies[2 * s] *= 0.5;
+            energies[2 * s + 1] = (c->prm.solver == CPIC_SOLVER_EM) ? 0.5 * energies[2 * s + 1] : 0.0;
+        }
+    }
+    if (en) { cudaStreamSynchronize(c->stream); cudaFree(en); }
+    return rc;
+}
+
+int cpic_push_stats_get(cpic_ctx* ctx, cpic_push_stats* out) {
+    CTX_OR_FAIL(ctx);
+    if (!out) return c->fail(CPIC_E_INVALID, "push_stats_get: null");
+    unsigned long long h[8];
+    int rc = c->cuda(cudaMemcpyAsync(h, c->stats_dev(), sizeof h, cudaMemcpyDeviceToHost, c->stream), "D2H stats");
+    if (rc) return rc;
+    if ((rc = c->cuda(cudaStreamSynchronize(c->stream), "push_stats"))) return rc;
+    out->movers = (int64_t)h[0]; out->crossings = (int64_t)h[1];
+    for (int i = 0; i < 6; ++i) out->wraps[i] = (int64_t)h[2 + i];
+    return CPIC_OK;
+}
+
+int cpic_device_ptr(cpic_ctx* ctx, int which, void** ptr, int64_t* count, int64_t* stride) {
+    CTX_OR_FAIL(ctx);
+    if (!ptr) return c->fail(CPIC_E_INVALID, "device_ptr: null");
+    return c->device_ptr(which, ptr, count, stride);
+}
+
+int cpic_set_stream(cpic_ctx* ctx, void* cuda_stream) {
+    CTX_OR_FAIL(ctx);
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+    return CPIC_OK;
+}
+
+int cpic_set_num_particles(cpic_ctx* ctx, int64_t n) {
+    CTX_OR_FAIL(ctx);
+    if (n < 0 || n > c->prm.max_particles) return c->fail(CPIC_E_CAPACITY, "set_num_particles: %lld out of range", (long long)n);
+    c->np = n;
+    return CPIC_OK;
+}
+
+int cpic_set_modes(cpic_ctx* ctx, int32_t fp_mode, int32_t deposit_mode) {
+    CTX_OR_FAIL(ctx);
+    if ((fp_mode != CPIC_FP_STRICT && fp_mode != CPIC_FP_CONTRACT) || deposit_mode < 0 || deposit_mode > 3)
+        return c->fail(CPIC_E_INVALID, "set_modes: bad mode");
+    c->prm.fp_mode = fp_mode;
+    c->prm.deposit_mode = deposit_mode;
+    return CPIC_OK;
+}
+
+int cpic_enable_push_stats(cpic_ctx* ctx, int32_t on) {
+    CTX_OR_FAIL(ctx);
+    c->want_stats = on != 0;
+    return CPIC_OK;
+}
+
+int cpic_last_ms(cpic_ctx* ctx, int what, double* ms) {
+    CTX_OR_FAIL(ctx);
+    if (!ms || what < 0 || what > 3) return c->fail(CPIC_E_INVALID, "last_ms: bad arguments");
+    if (!c->ev_valid[what]) return c->fail(CPIC_E_INVALID, "last_ms: nothing recorded for %d", what);
+    int rc = c->cuda(cudaEventSynchronize(c->ev[2 * what + 1]), "cudaEventSynchronize");
+    if (rc) return rc;
+    float f = 0.f;
+    if ((rc = c->cuda(cudaEventElapsedTime(&f, c->ev[2 * what], c->ev[2 * what + 1]), "cudaEventElapsedTime"))) return rc;
+    *ms = f;
+    return CPIC_OK;
+}
+
+int cpic_launch_count(cpic_ctx* ctx, int64_t* launches) {
+    CTX_OR_FAIL(ctx);
+    if (!launches) return c->fail(CPIC_E_INVALID, "launch_count: null");
+    *launches = c->launches;
+    return CPIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Device-side particle initialiser for the synthetic uniform thermal plasma.
+// The reference runs its default initialisers in the execution space as well
+// (Cabana::simd_parallel_for in src/input/deck.h:155-157); decks that need host code
+// (rand(), std::cout) keep using the host path + cpic_upload_particles.
+//
+// Counter-based RNG: Philox-4x32-10 keyed by the seed, counter = global particle index, so
+// every GPU (and the numpy mirror in cabanapic_b200/decks.py, which consumes the same
+// words in the same roles) can generate any slice of the global particle list independently.
+#pragma once
+#include "cpic_common.cuh"
+#include "cpic_particles.cuh"
+
+namespace cpic {
+
+__device__ __forceinline__ void philox4x32_10(unsigned long long ctr, unsigned stream, unsigned long long key,
+                                              unsigned (&out)[4]) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    unsigned x0 = (unsigned)ctr, x1 = (unsigned)(ctr >> 32), x2 = stream, x3 = 0u;
+    unsigned k0 = (unsigned)key, k1 = (unsigned)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(M0, x0), lo0 = M0 * x0;
+        const unsigned hi1 = __umulhi(M1, x2), lo1 = M1 * x2;
+        const unsigned n0 = hi1 ^ x1 ^ k0, n2 = hi0 ^ x3 ^ k1;
+        x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+}
+
+__device__ __forceinline__ double u01(unsigned v) { return ((double)v + 0.5) * (1.0 / 4294967296.0); }
+
+struct UniformPlasmaArgs {
+    long long first, count;   // global particle indices [first, first+count)
+    int gnx, gny, gnz;        // global interior grid
+    int nppc;
+    int z0;                   // first global interior z-plane owned by this context (slab mode), else 0
+    int lnx, lny;             // local interior extents in x, y (== global)
+    unsigned long long seed;
+    double vth[3];
+    double weight;
+};
+
+// Particle k sits in global interior cell k / nppc (x fastest): the store starts cell-sorted.
+// Offsets ~ U(-1,1); momenta ~ N(0, vth) by Box-Muller, evaluated in double then narrowed.
+template <class R>
+__global__ void __launch_bounds__(256) k_init_uniform_plasma(Particles<R> p, UniformPlasmaArgs a) {
+    const long long n = blockIdx.x * 256LL + threadIdx.x;
+    if (n >= a.count) return;
+    const unsigned long long k = (unsigned long long)(a.first + n);
+    unsigned ra[4], rb[4];
+    philox4x32_10(k, 0u, a.seed, ra);
+    philox4x32_10(k, 1u, a.seed, rb);
+    p.dx[n] = (R)(2.0 * u01(ra[0]) - 1.0);
+    p.dy[n] = (R)(2.0 * u01(ra[1]) - 1.0);
+    p.dz[n] = (R)(2.0 * u01(ra[2]) - 1.0);
+    const double r1 = sqrt(-2.0 * log(u01(ra[3])));
+    const double r2 = sqrt(-2.0 * log(u01(rb[0])));
+    const double t1 = 6.283185307179586 * u01(rb[1]);
+    const double t2 = 6.283185307179586 * u01(rb[2]);
+    p.ux[n] = (R)(a.vth[0] * r1 * cos(t1));
+    p.uy[n] = (R)(a.vth[1] * r1 * sin(t1));
+    p.uz[n] = (R)(a.vth[2] * r2 * cos(t2));
+    p.w[n] = (R)a.weight;
+    const long long c = (long long)(k / (unsigned long long)a.nppc);
+    const int ix = (int)(c % a.gnx);
+    const int iy = (int)((c / a.gnx) % a.gny);
+    const int iz = (int)(c / ((long long)a.gnx * a.gny));
+    p.cell[n] = (ix + 1) + (a.lnx + 2) * ((iy + 1) + (a.lny + 2) * (iz - a.z0 + 1));
+}
+
+}  // namespace cpic

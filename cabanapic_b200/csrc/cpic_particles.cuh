@@ -1,0 +1,414 @@
+// Particle kernels: Boris push + VPIC-style cell-crossing mover + current deposit, and
+// the one-off uncenter rotation.
+//
+// Reference: push<>, src/push.h:65-295; move_p<>, src/move_p.h:59-374 (with
+// detect_leaving_domain :9-54); uncenter_particles, src/uncenter_p.h:27-98.
+//
+// Layout: particles are struct-of-arrays (8 member arrays), one thread per particle, so a
+// warp reads/writes 32 consecutive elements of each member (fully coalesced).  The
+// interpolator record of the particle's cell is fetched with 128-bit loads through the
+// read-only path (cell-sorted particles make these warp-wide broadcasts of one record).
+//
+// Deposit: every streak adds 12 values (jx[4] jy[4] jz[4]) to its cell's accumulator row.
+// The first streak of every particle -- the only one for the ~87 % that stay in their
+// cell -- goes to the particle's *current* cell, so for cell-sorted particles a whole
+// warp targets one row: the warp transposes-and-reduces the 12x32 values with 16 shuffles
+// and issues ONE 12-lane atomic row update instead of 384 atomics.  Later streaks of cell
+// crossers (rare, scattered over the 6 neighbours) use 128-bit vector atomics directly.
+#pragma once
+#include "cpic_common.cuh"
+
+namespace cpic {
+
+template <class R>
+struct Particles {
+    R *dx, *dy, *dz, *ux, *uy, *uz, *w;
+    int* cell;
+};
+
+template <class R>
+struct PushArgs {
+    Particles<R> p;
+    long long np;
+    const R* ip;   // [nc][IpStride]
+    R* acc;        // [nc][12]
+    R qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
+    int nx, ny, nz, ng, gx, gy;
+    int periodic;
+    unsigned long long* stats;  // optional: [0] movers [1] crossings [2..7] wraps per face
+};
+
+// ---------------------------------------------------------------------------------------
+// The 12 quadrant currents of one streak.  Reference: CALC_J, src/push.h:218-232 and
+// accumulate_j, src/move_p.h:156-170 (identical arithmetic).  d = streak midpoint,
+// u = half displacement in cell units, v5 = the q*ux*uy*uz/3 correction.
+template <bool FMA, class R>
+__device__ __forceinline__ void streak_currents(R q, R ux, R uy, R uz, R dx, R dy, R dz, R v5, R (&a)[12]) {
+    const R one = R(1);
+#define CPIC_QUAD(U, DA, DB, O)                                   \
+    {                                                             \
+        R v0, v1, v2, v3, v4;                                     \
+        v4 = q * (U);                                             \
+        if constexpr (FMA) {                                      \
+            v0 = madd<true>(-v4, (DA), v4);                       \
+            v1 = madd<true>(v4, (DA), v4);                        \
+            const R hi = one + (DB), lo = one - (DB);             \
+            v2 = madd<true>(v0, hi, -v5);                         \
+            v3 = madd<true>(v1, hi, v5);                          \
+            v0 = madd<true>(v0, lo, v5);                          \
+            v1 = madd<true>(v1, lo, -v5);                         \
+        } else {                                                  \
+            v1 = v4 * (DA);                                       \
+            v0 = v4 - v1;                                         \
+            v1 += v4;                                             \
+            v4 = one + (DB);                                      \
+            v2 = v0 * v4;                                         \
+            v3 = v1 * v4;                                         \
+            v4 = one - (DB);                                      \
+            v0 *= v4;                                             \
+            v1 *= v4;                                             \
+            v0 += v5;                                             \
+            v1 -= v5;                                             \
+            v2 -= v5;                                             \
+            v3 += v5;                                             \
+        }                                                         \
+        a[(O) + 0] = v0; a[(O) + 1] = v1; a[(O) + 2] = v2; a[(O) + 3] = v3; \
+    }
+    CPIC_QUAD(ux, dy, dz, 0)
+    CPIC_QUAD(uy, dz, dx, 4)
+    CPIC_QUAD(uz, dx, dy, 8)
+#undef CPIC_QUAD
+}
+
+// ---------------------------------------------------------------------------------------
+// Accumulator row updates.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+}
+template <class R>
+__device__ __forceinline__ void row_add_scalar(R* row, const R (&a)[12]) {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) atomicAdd(row + j, a[j]);
+}
+__device__ __forceinline__ void row_add_vec(float* row, const float (&a)[12]) {
+    red_add_v4(row + 0, a[0], a[1], a[2], a[3]);
+    red_add_v4(row + 4, a[4], a[5], a[6], a[7]);
+    red_add_v4(row + 8, a[8], a[9], a[10], a[11]);
+}
+__device__ __forceinline__ void row_add_vec(double* row, const double (&a)[12]) { row_add_scalar(row, a); }
+
+// Sum a[0..11] over the lanes in `mask`-selected contributions (others pass zeros) with a
+// transpose-reduce: after the 5 exchange stages lane L holds the warp total of entry
+// e(L) = 8*b4 + 4*b3 + 2*b2 + b1 (b_k = bit k of L); lanes with bit 0 set hold duplicates.
+template <class R>
+__device__ __forceinline__ R warp_transpose_sum12(const R (&a)[12], int lane) {
+    const unsigned full = 0xffffffffu;
+    R r8[8], r4[4], r2[2], r1;
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const R lo = a[j], hi = (j + 8 < 12) ? a[j + 8] : R(0);
+        const R keep = h4 ? hi : lo, send = h4 ? lo : hi;
+        r8[j] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const R keep = h3 ? r8[j + 4] : r8[j], send = h3 ? r8[j] : r8[j + 4];
+        r4[j] = keep + __shfl_xor_sync(full, send, 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const R keep = h2 ? r4[j + 2] : r4[j], send = h2 ? r4[j] : r4[j + 2];
+        r2[j] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    {
+        const R keep = h1 ? r2[1] : r2[0], send = h1 ? r2[0] : r2[1];
+        r1 = keep + __shfl_xor_sync(full, send, 2);
+    }
+    r1 += __shfl_xor_sync(full, r1, 1);
+    return r1;
+}
+
+// First-streak deposit; must be called by all 32 lanes of the warp (converged).
+template <class R, int DEPOSIT>
+__device__ __forceinline__ void deposit_first(R* __restrict__ acc, bool valid, int ii, const R (&a)[12], int lane) {
+    if constexpr (DEPOSIT == 1) {
+        if (valid) row_add_scalar(acc + (long long)ii * 12, a);
+    } else if constexpr (DEPOSIT == 2) {
+        if (valid) row_add_vec(acc + (long long)ii * 12, a);
+    } else {
+        const unsigned full = 0xffffffffu;
+        const unsigned vmask = __ballot_sync(full, valid);
+        if (vmask == 0) return;
+        const int leader = __ffs(vmask) - 1;
+        const int c0 = __shfl_sync(full, ii, leader);
+        unsigned same = __ballot_sync(full, valid && ii == c0);
+        const int e = ((lane >> 1) & 7) | ((lane & 16) >> 1);  // entry this lane ends up holding
+        if (same == vmask) {  // the common case for cell-sorted particles: one row per warp
+            R z[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) z[j] = valid ? a[j] : R(0);
+            const R tot = warp_transpose_sum12(z, lane);
+            if (!(lane & 1) && e < 12) atomicAdd(acc + (long long)c0 * 12 + e, tot);
+            return;
+        }
+        // Mixed warp: peel off one cell at a time while groups are big enough to be worth a
+        // warp reduction; the remaining stragglers update their rows directly.
+        unsigned todo = vmask;
+        bool mine_done = !valid;
+        int guard = 0;
+        while (todo) {
+            const int ld = __ffs(todo) - 1;
+            const int c = __shfl_sync(full, ii, ld);
+            const bool mine = !mine_done && ii == c;
+            const unsigned grp = __ballot_sync(full, mine);
+            if (__popc(grp) >= 6 && guard < 4) {
+                R z[12];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) z[j] = mine ? a[j] : R(0);
+                const R tot = warp_transpose_sum12(z, lane);
+                if (!(lane & 1) && e < 12) atomicAdd(acc + (long long)c * 12 + e, tot);
+                if (mine) mine_done = true;
+                todo &= ~grp;
+                ++guard;
+            } else {
+                break;
+            }
+        }
+        if (!mine_done) row_add_vec(acc + (long long)ii * 12, a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// One streak of the mover.  Reference: src/move_p.h:101-137,154,195-203.  On entry (x,y,z)
+// is the stored position and (rx,ry,rz) the remaining half displacement; on exit the
+// position has advanced by twice the streak, the remainder has shrunk, (sx..,mx..,v5) describe
+// the streak, and the return value is the axis whose face ended it (3 = end of track).
+// The bare literals 3.4e38, 2, 0.5 and (1./3.) of the reference are doubles/ints mixed into
+// real_t arithmetic; only the last one changes a rounding (final multiply in double).
+template <class R>
+__device__ __forceinline__ int mover_streak(R& x, R& y, R& z, R& rx, R& ry, R& rz, R q, R& sx, R& sy, R& sz,
+                                            R& mx, R& my, R& mz, R& v5, R& dirv) {
+    sx = rx; sy = ry; sz = rz;
+    const R d0 = (sx > 0) ? R(1) : R(-1);
+    const R d1 = (sy > 0) ? R(1) : R(-1);
+    const R d2 = (sz > 0) ? R(1) : R(-1);
+    const R big = R(3.4e38);
+    const R v0 = (sx == 0) ? big : (d0 - x) / sx;
+    const R v1 = (sy == 0) ? big : (d1 - y) / sy;
+    const R v2 = (sz == 0) ? big : (d2 - z) / sz;
+    R v3 = R(2);
+    int axis = 3;
+    if (v0 < v3) { v3 = v0; axis = 0; }
+    if (v1 < v3) { v3 = v1; axis = 1; }
+    if (v2 < v3) { v3 = v2; axis = 2; }
+    v3 *= R(0.5);
+    sx *= v3; sy *= v3; sz *= v3;
+    mx = x + sx; my = y + sy; mz = z + sz;
+    v5 = (R)((double)(q * sx * sy * sz) * (1. / 3.));
+    rx -= sx; ry -= sy; rz -= sz;
+    x += sx + sx; y += sy + sy; z += sz + sz;
+    dirv = (axis == 0) ? d0 : (axis == 1 ? d1 : d2);
+    return axis;
+}
+
+// Cell update when a streak ended on a face.  Reference: src/move_p.h:218-244 (neighbour),
+// :9-54 (ghost-layer test, later tests override earlier, one ghost layer assumed),
+// :257-288 (periodic wrap), :351-352 (new voxel).  Returns the face code 0..5 (-x -y -z +x +y +z)
+// in the low bits and, if the neighbour was a ghost layer, 8 + that layer's code above them.
+template <class R>
+__device__ __forceinline__ int cross_face(int& ii, int axis, R dirv, const PushArgs<R>& a) {
+    int face = axis;
+    if (dirv > 0) face += 3;
+    int iy = ii / a.gx;
+    int ix = ii - iy * a.gx;
+    int iz = iy / a.gy;
+    iy -= iz * a.gy;
+    if (face == 0) ix--;
+    if (face == 1) iy--;
+    if (face == 2) iz--;
+    if (face == 3) ix++;
+    if (face == 4) iy++;
+    if (face == 5) iz++;
+    int leaving = -1;
+    if (ix == 0) leaving = 0;
+    if (iy == 0) leaving = 1;
+    if (iz == 0) leaving = 2;
+    if (ix == a.nx + 1) leaving = 3;
+    if (iy == a.ny + 1) leaving = 4;
+    if (iz == a.nz + 1) leaving = 5;
+    if (leaving >= 0 && a.periodic) {
+        if (leaving == 0) ix = (a.nx - 1) + a.ng;
+        else if (leaving == 1) iy = (a.ny - 1) + a.ng;
+        else if (leaving == 2) iz = (a.nz - 1) + a.ng;
+        else if (leaving == 3) ix = a.ng;
+        else if (leaving == 4) iy = a.ng;
+        else iz = a.ng;
+    }
+    ii = ix + a.gx * (iy + a.gy * iz);
+    return face | (leaving >= 0 ? ((8 + leaving) << 4) : 0);
+}
+
+// Load the (padded) interpolator record of cell ii with 128-bit read-only loads.
+template <class R>
+__device__ __forceinline__ void load_record(const R* __restrict__ ip, int ii, R (&f)[IpStride<R>::value]) {
+    constexpr int S = IpStride<R>::value;
+    using V = typename std::conditional<sizeof(R) == 4, float4, double2>::type;
+    constexpr int PER = 16 / sizeof(R);
+    const V* src = reinterpret_cast<const V*>(ip + (long long)ii * S);
+#pragma unroll
+    for (int k = 0; k < S / PER; ++k) {
+        const V v = __ldg(src + k);
+        *reinterpret_cast<V*>(&f[k * PER]) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+template <class R, bool FMA, int DEPOSIT, bool STATS>
+__global__ void __launch_bounds__(256) k_push(PushArgs<R> a) {
+    const long long n = blockIdx.x * 256LL + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = n < a.np;
+    const R one = R(1.), one_third = R(1. / 3.), two_fifteenths = R(2. / 15.);
+
+    int ii = 0;
+    bool mover = false;
+    int axis = 3;
+    R x = 0, y = 0, z = 0;        // stored position (updated as the mover advances)
+    R rx = 0, ry = 0, rz = 0;     // remaining half displacement (mover only)
+    R q = 0, dirv = 0;
+    R cur[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) cur[j] = R(0);
+
+    if (valid) {
+        ii = a.p.cell[n];
+        R f[IpStride<R>::value];
+        load_record(a.ip, ii, f);
+        x = a.p.dx[n]; y = a.p.dy[n]; z = a.p.dz[n];
+        R ux = a.p.ux[n], uy = a.p.uy[n], uz = a.p.uz[n];
+        q = a.p.w[n] * a.qsp;
+
+        // src/push.h:124-138 -- trilinear E, linear B at the particle
+        const R hax = a.qdt_2mc * madd<FMA>(z, madd<FMA>(y, f[I_D2EXDYDZ], f[I_DEXDZ]), madd<FMA>(y, f[I_DEXDY], f[I_EX]));
+        const R hay = a.qdt_2mc * madd<FMA>(x, madd<FMA>(z, f[I_D2EYDZDX], f[I_DEYDX]), madd<FMA>(z, f[I_DEYDZ], f[I_EY]));
+        const R haz = a.qdt_2mc * madd<FMA>(y, madd<FMA>(x, f[I_D2EZDXDY], f[I_DEZDY]), madd<FMA>(x, f[I_DEZDX], f[I_EZ]));
+        const R cbx = madd<FMA>(x, f[I_DCBXDX], f[I_CBX]);
+        const R cby = madd<FMA>(y, f[I_DCBYDY], f[I_CBY]);
+        const R cbz = madd<FMA>(z, f[I_DCBZDZ], f[I_CBZ]);
+
+        ux += hax; uy += hay; uz += haz;                                  // half E kick, :144-146
+        // :148 -- sqrtf even when real_t is double (argument rounds to float first)
+        R v0 = a.qdt_2mc / (R)sqrtf((float)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));
+        R v1 = madd<FMA>(cbx, cbx, madd<FMA>(cby, cby, cbz * cbz));
+        R v2 = (v0 * v0) * v1;
+        R v3 = v0 * madd<FMA>(v2, madd<FMA>(v2, two_fifteenths, one_third), one);
+        R v4 = v3 / madd<FMA>(v1, v3 * v3, one);
+        v4 += v4;
+        v0 = madd<FMA>(v3, mdiff<FMA>(uy, cbz, uz, cby), ux);              // Boris u', :155-157
+        v1 = madd<FMA>(v3, mdiff<FMA>(uz, cbx, ux, cbz), uy);
+        v2 = madd<FMA>(v3, mdiff<FMA>(ux, cby, uy, cbx), uz);
+        ux = madd<FMA>(v4, mdiff<FMA>(v1, cbz, v2, cby), ux);              // rotation, :158-160
+        uy = madd<FMA>(v4, mdiff<FMA>(v2, cbx, v0, cbz), uy);
+        uz = madd<FMA>(v4, mdiff<FMA>(v0, cby, v1, cbx), uz);
+        ux += hax; uy += hay; uz += haz;                                  // second half kick
+        a.p.ux[n] = ux; a.p.uy[n] = uy; a.p.uz[n] = uz;                   // :165-167
+
+        v0 = one / (R)sqrtf((float)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));  // :169
+        ux *= a.cdt_dx; uy *= a.cdt_dy; uz *= a.cdt_dz;                   // this order, :171-176
+        ux *= v0; uy *= v0; uz *= v0;
+        v0 = x + ux; v1 = y + uy; v2 = z + uz;                            // streak midpoint
+        v3 = v0 + ux; v4 = v1 + uy;                                       // new position
+        const R v5n = v2 + uz;
+
+        if (v3 <= one && v4 <= one && v5n <= one && -v3 <= one && -v4 <= one && -v5n <= one) {  // :187
+            a.p.dx[n] = v3; a.p.dy[n] = v4; a.p.dz[n] = v5n;
+            const R v5 = q * ux * uy * uz * one_third;                    // :203
+            streak_currents<FMA>(q, ux, uy, uz, v0, v1, v2, v5, cur);
+        } else {
+            mover = true;
+            rx = ux; ry = uy; rz = uz;                                    // local_pm, :261-263
+            R sx, sy, sz, mx, my, mz, v5;
+            axis = mover_streak(x, y, z, rx, ry, rz, q, sx, sy, sz, mx, my, mz, v5, dirv);
+            streak_currents<FMA>(q, sx, sy, sz, mx, my, mz, v5, cur);
+        }
+    }
+
+    // first streak of every particle lands in the particle's current cell
+    deposit_first<R, DEPOSIT>(a.acc, valid, ii, cur, lane);
+
+    unsigned long long n_cross = 0, n_wrap[6] = {0, 0, 0, 0, 0, 0};
+    if (mover) {
+        while (axis != 3) {
+            // snap onto the face, move to the neighbour, re-enter from its other side
+            const int code = cross_face(ii, axis, dirv, a);
+            if (axis == 0) x = -dirv;
+            if (axis == 1) y = -dirv;
+            if (axis == 2) z = -dirv;
+            if (STATS) {
+                ++n_cross;
+                if (code >> 4) ++n_wrap[(code >> 4) - 8];
+            }
+            R sx, sy, sz, mx, my, mz, v5;
+            axis = mover_streak(x, y, z, rx, ry, rz, q, sx, sy, sz, mx, my, mz, v5, dirv);
+            streak_currents<FMA>(q, sx, sy, sz, mx, my, mz, v5, cur);
+            if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)ii * 12, cur);
+            else row_add_vec(a.acc + (long long)ii * 12, cur);
+        }
+        a.p.dx[n] = x; a.p.dy[n] = y; a.p.dz[n] = z;
+        a.p.cell[n] = ii;
+    }
+
+    if (STATS) {
+        const unsigned full = 0xffffffffu;
+        unsigned long long v[8];
+        v[0] = mover ? 1ull : 0ull; v[1] = n_cross;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[2 + k] = n_wrap[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(full, v[k], o);
+            if (lane == 0 && v[k]) atomicAdd(a.stats + k, v[k]);
+        }
+    }
+}
+
+// Reference: uncenter_particles, src/uncenter_p.h:27-98 -- backward half Boris rotation
+// (qdt_4mc = -0.5*qdt_2mc) followed by one +half E kick; positions untouched.  Uses sqrt in
+// real_t here (the reference casts a double sqrt), not sqrtf.
+template <class R, bool FMA>
+__global__ void __launch_bounds__(256) k_uncenter(Particles<R> p, long long np, const R* __restrict__ ip, R qdt_2mc) {
+    const long long n = blockIdx.x * 256LL + threadIdx.x;
+    if (n >= np) return;
+    const R one = R(1.), one_third = R(1. / 3.), two_fifteenths = R(2. / 15.);
+    const R qdt_4mc = (R)(-0.5 * (double)qdt_2mc);
+    R f[IpStride<R>::value];
+    load_record(ip, p.cell[n], f);
+    const R x = p.dx[n], y = p.dy[n], z = p.dz[n];
+    const R hax = qdt_2mc * madd<FMA>(z, madd<FMA>(y, f[I_D2EXDYDZ], f[I_DEXDZ]), madd<FMA>(y, f[I_DEXDY], f[I_EX]));
+    const R hay = qdt_2mc * madd<FMA>(x, madd<FMA>(z, f[I_D2EYDZDX], f[I_DEYDX]), madd<FMA>(z, f[I_DEYDZ], f[I_EY]));
+    const R haz = qdt_2mc * madd<FMA>(y, madd<FMA>(x, f[I_D2EZDXDY], f[I_DEZDY]), madd<FMA>(x, f[I_DEZDX], f[I_EZ]));
+    const R cbx = madd<FMA>(x, f[I_DCBXDX], f[I_CBX]);
+    const R cby = madd<FMA>(y, f[I_DCBYDY], f[I_CBY]);
+    const R cbz = madd<FMA>(z, f[I_DCBZDZ], f[I_CBZ]);
+    R ux = p.ux[n], uy = p.uy[n], uz = p.uz[n];
+    R v0 = qdt_4mc / (R)sqrt((double)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));
+    R v1 = madd<FMA>(cbx, cbx, madd<FMA>(cby, cby, cbz * cbz));
+    R v2 = (v0 * v0) * v1;
+    R v3 = v0 * madd<FMA>(v2, madd<FMA>(v2, two_fifteenths, one_third), one);
+    R v4 = v3 / madd<FMA>(v1, v3 * v3, one);
+    v4 += v4;
+    v0 = madd<FMA>(v3, mdiff<FMA>(uy, cbz, uz, cby), ux);
+    v1 = madd<FMA>(v3, mdiff<FMA>(uz, cbx, ux, cbz), uy);
+    v2 = madd<FMA>(v3, mdiff<FMA>(ux, cby, uy, cbx), uz);
+    ux = madd<FMA>(v4, mdiff<FMA>(v1, cbz, v2, cby), ux);
+    uy = madd<FMA>(v4, mdiff<FMA>(v2, cbx, v0, cbz), uy);
+    uz = madd<FMA>(v4, mdiff<FMA>(v0, cby, v1, cbx), uz);
+    ux += hax; uy += hay; uz += haz;
+    p.ux[n] = ux; p.uy[n] = uy; p.uz[n] = uz;
+}
+
+}  // namespace cpic

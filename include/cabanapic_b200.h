@@ -1,0 +1,172 @@
+/*
+ * cabanapic_b200 -- C ABI of the B200-native CabanaPIC particle hot path.
+ *
+ * The reference (ECP-copa/CabanaPIC) has no FFI layer: its hot path sits behind
+ * plain C++ free functions called from example/example.cpp.  Every entry point
+ * below replaces one of those call sites (cited as path:line relative to the
+ * reference tree) and is what a reference-side binding would call; see
+ * INTEGRATION.md for the stub a maintainer would add.
+ *
+ * Conventions
+ *   - opaque context, one host thread per context, one CUDA device per context;
+ *   - every function returns 0 on success or a negative CPIC_E_* code;
+ *     cpic_last_error(ctx) gives the message (no exceptions cross the boundary);
+ *   - work is enqueued in order on the context's stream; only download_*,
+ *     energies, migration/query calls and cpic_sync block the host;
+ *   - `real` buffers are float or double according to cpic_params.real_bytes
+ *     (the reference's -DREAL_TYPE, src/types.h:4-8), passed as void*;
+ *   - particle members are the reference's AoSoA members (src/types.h:31-58):
+ *     dx dy dz (cell-local offset in [-1,1]), ux uy uz (momentum), w, cell
+ *     (int voxel index incl. ghosts, VOXEL() of src/types.h:195);
+ *   - field members in FieldFields order (src/types.h:138-149):
+ *     ex ey ez cbx cby cbz jfx jfy jfz, each num_cells long;
+ *   - interpolators are exchanged as [cell][18] (src/types.h:64-84),
+ *     accumulators as [cell][3][4] (src/types.h:116-120).
+ * There is no CPU fallback: creating a context without a usable CUDA device
+ * fails with CPIC_E_CUDA.
+ */
+#ifndef CABANAPIC_B200_H
+#define CABANAPIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPIC_ABI_VERSION 1
+
+enum {
+    CPIC_OK = 0,
+    CPIC_E_INVALID = -1,     /* bad argument / unsupported configuration     */
+    CPIC_E_CUDA = -2,        /* CUDA runtime error (message has the detail)  */
+    CPIC_E_NOMEM = -3,       /* device allocation failed                     */
+    CPIC_E_CAPACITY = -4,    /* more particles than max_particles            */
+    CPIC_E_BAD_CELL = -5,    /* particle cell index outside the grid         */
+    CPIC_E_UNSUPPORTED = -6  /* e.g. Boundary::Reflect (reference: exit(1))  */
+};
+
+enum { CPIC_SOLVER_EM = 0, CPIC_SOLVER_ES_1D = 1 };   /* -DSOLVER_TYPE, example/example.cpp:24-35 */
+enum { CPIC_BOUNDARY_REFLECT = 0, CPIC_BOUNDARY_PERIODIC = 1 }; /* enum Boundary, src/input/deck.h:9-12 */
+
+/* Floating-point policy of the particle kernels.
+ * STRICT: every multiply/add rounds separately, IEEE sqrt/div -- bit-identical
+ *         per-particle results to the reference's CPU build (gcc -O2, no FMA).
+ * CONTRACT: a*b+c chains are fused (what nvcc does to the reference's Kokkos-CUDA
+ *         build by default); results agree to rounding, not bitwise. */
+enum { CPIC_FP_STRICT = 0, CPIC_FP_CONTRACT = 1 };
+
+/* How push() adds the 12 per-streak currents into the accumulator.
+ * All modes give the same sums up to floating-point association. */
+enum {
+    CPIC_DEPOSIT_AUTO = 0,        /* = WARP                                               */
+    CPIC_DEPOSIT_ATOMIC = 1,      /* 12 scalar global atomics per streak                  */
+    CPIC_DEPOSIT_ATOMIC_V4 = 2,   /* 3 x 128-bit vector atomics per streak (float only)   */
+    CPIC_DEPOSIT_WARP = 3         /* warp-aggregated per cell, then one atomic row/warp   */
+};
+
+typedef struct cpic_ctx cpic_ctx;
+
+typedef struct cpic_params {
+    int32_t nx, ny, nz, ng;       /* interior cells per axis; ng must be 1 (src/move_p.h:19-47 hard-wires it) */
+    int32_t real_bytes;           /* 4 or 8 */
+    int32_t solver;               /* CPIC_SOLVER_* */
+    int32_t boundary;             /* CPIC_BOUNDARY_* */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t fp_mode;              /* CPIC_FP_* */
+    int32_t deposit_mode;         /* CPIC_DEPOSIT_* */
+    int64_t max_particles;        /* capacity of the particle store */
+    int32_t enable_sort;          /* allocate the second particle buffer needed by cpic_sort_particles */
+    int32_t reserved[7];
+} cpic_params;
+
+/* Step constants exactly as the reference driver derives them in real_t
+ * (example/example.cpp:77-113, 179-181), widened to double for transport. */
+typedef struct cpic_consts {
+    double qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
+    double dx, dy, dz, dt;
+    double px, py, pz, dt_eps0;
+} cpic_consts;
+
+/* Diagnostics of the last push (optional). */
+typedef struct cpic_push_stats {
+    int64_t movers;     /* particles that left their cell (took the move_p path) */
+    int64_t crossings;  /* total cell faces crossed                               */
+    int64_t wraps[6];   /* periodic wraps per face: -x -y -z +x +y +z              */
+} cpic_push_stats;
+
+int  cpic_abi_version(void);
+const char* cpic_last_error(const cpic_ctx* ctx);   /* ctx may be NULL: error of the last failed cpic_create */
+
+/* particle_list_t / field_array_t / interpolator_array_t / accumulator_array_t
+ * allocation, example/example.cpp:121-144; Field_Solver ctor zeroing, src/fields.h:279-315;
+ * initialize_interpolator, src/interpolator.cpp:125-172. */
+int  cpic_create(const cpic_params* params, cpic_ctx** out);
+void cpic_destroy(cpic_ctx* ctx);
+int  cpic_sync(cpic_ctx* ctx);
+int  cpic_num_cells(const cpic_ctx* ctx, int64_t* out);
+int  cpic_num_particles(const cpic_ctx* ctx, int64_t* out);
+
+/* Deck initialisers run on the host (src/input/deck.h:209-252); these move the result. */
+int  cpic_upload_particles(cpic_ctx* ctx, const void* dx, const void* dy, const void* dz, const void* ux,
+                           const void* uy, const void* uz, const void* w, const int32_t* cell, int64_t n);
+int  cpic_download_particles(cpic_ctx* ctx, void* dx, void* dy, void* dz, void* ux, void* uy, void* uz, void* w,
+                             int32_t* cell, int64_t capacity, int64_t* n_out);
+int  cpic_upload_fields(cpic_ctx* ctx, const void* const fields[9]);
+int  cpic_download_fields(cpic_ctx* ctx, void* const fields[9]);
+int  cpic_upload_interpolators(cpic_ctx* ctx, const void* interp /* [nc][18] */);
+int  cpic_download_interpolators(cpic_ctx* ctx, void* interp /* [nc][18] */);
+int  cpic_upload_accumulators(cpic_ctx* ctx, const void* acc /* [nc][12] */);
+int  cpic_download_accumulators(cpic_ctx* ctx, void* acc /* [nc][12] */);
+
+/* The time-loop call surface, example/example.cpp:221-266 */
+int  cpic_load_interpolator_array(cpic_ctx* ctx);                 /* src/interpolator.cpp:4-124   */
+int  cpic_initialize_interpolator(cpic_ctx* ctx);                 /* src/interpolator.cpp:125-172 */
+int  cpic_clear_accumulator_array(cpic_ctx* ctx);                 /* src/accumulator.cpp:5-43     */
+int  cpic_push(cpic_ctx* ctx, const cpic_consts* k);              /* src/push.h:7-300 + src/move_p.h:59-374 */
+int  cpic_contribute(cpic_ctx* ctx);                              /* Kokkos contribute/reset_except, example.cpp:248-251 (no-op on one GPU) */
+int  cpic_unload_accumulator_array(cpic_ctx* ctx, const cpic_consts* k); /* src/accumulator.cpp:45-122 */
+int  cpic_advance_b(cpic_ctx* ctx, double px, double py, double pz);     /* src/fields.h:352-364, 668-719 (ES: no-op) */
+int  cpic_advance_e(cpic_ctx* ctx, double px, double py, double pz, double dt_eps0); /* src/fields.h:365-378, 618-665, 511-544 */
+int  cpic_uncenter_particles(cpic_ctx* ctx, double qdt_2mc);      /* src/uncenter_p.h:4-105       */
+int  cpic_energies(cpic_ctx* ctx, double* e_energy, double* b_energy);   /* src/fields.h:556-615, 484-509 */
+int  cpic_update_ghosts(cpic_ctx* ctx, int which /* 0: fold J, 1: copy J, 2: copy cB */); /* src/fields.h:11-271 */
+
+/* n whole steps in the reference's order (example/example.cpp:221-266), fused on the
+ * device: no host synchronisation between steps.  sort_interval > 0 re-sorts the particles
+ * by cell every that many steps (the step the reference left commented out,
+ * example/example.cpp:224-228).  energies (optional, host) receives (e,b) after every step. */
+int  cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, double* energies);
+
+/* Device-side Particle_Initializer for the synthetic uniform thermal plasma (the reference's
+ * default initialisers also run in the execution space, src/input/deck.h:155-157): fills this
+ * context's store with global particles [first, first+count) of a gnx*gny*gnz*nppc box;
+ * particle k sits in global interior cell k/nppc (x fastest), offsets U(-1,1), momenta
+ * N(0,vth) from Philox-4x32-10(seed, k).  z0 = first global z-plane owned here (slab mode). */
+int  cpic_init_uniform_plasma(cpic_ctx* ctx, int64_t first, int64_t count, int32_t gnx, int32_t gny, int32_t gnz,
+                              int32_t nppc, int32_t z0, uint64_t seed, double vthx, double vthy, double vthz,
+                              double weight);
+
+/* Cabana::sortByKey by Cell_Index (example/example.cpp:224-228). */
+int  cpic_sort_particles(cpic_ctx* ctx);
+int  cpic_enable_push_stats(cpic_ctx* ctx, int32_t on);   /* count movers/crossings/wraps in cpic_push (off by default) */
+int  cpic_push_stats_get(cpic_ctx* ctx, cpic_push_stats* out);
+
+/* Interop for host frameworks that own streams / collectives (torch.distributed, NCCL):
+ * raw device pointers of the context's arrays.  which: 0..7 particle members,
+ * 16 fields (9*nc_pad contiguous, member m at offset m*stride), 17 interpolators, 18 accumulators. */
+int  cpic_device_ptr(cpic_ctx* ctx, int which, void** ptr, int64_t* count, int64_t* stride);
+int  cpic_set_stream(cpic_ctx* ctx, void* cuda_stream);
+int  cpic_set_num_particles(cpic_ctx* ctx, int64_t n);   /* after an external particle exchange */
+int  cpic_set_modes(cpic_ctx* ctx, int32_t fp_mode, int32_t deposit_mode);
+
+/* Device-side timing of the last call of each kind, in milliseconds (CUDA events on the
+ * context's stream).  what: 0 push, 1 sort, 2 field side (interp+unload+advance), 3 step total. */
+int  cpic_last_ms(cpic_ctx* ctx, int what, double* ms);
+int  cpic_launch_count(cpic_ctx* ctx, int64_t* launches);  /* kernels launched by this ctx so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CABANAPIC_B200_H */
