@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the CabanaPIC particle hot path on B200 (contract: see the build prompt).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N ...            # reference CPU arm (rank 0 only)
+
+metric    particle-steps/s of the whole time step (sort + interpolator load + push/move/deposit
+          + accumulator unload + Yee field advance) on the synthetic uniform thermal plasma of
+          BASELINE.json configs[4] / SURVEY.md §8(d): 256^3 cells x 64 particles/cell = 2^30
+          particles, float, periodic, vth = 0.1 c, dt = 0.99 Courant.
+value     device-resident throughput (state already in HBM), CUDA events on the context's stream.
+e2e       the same metric through the C-ABI with HOST buffers: every e2e step uploads the whole
+          particle + field state from pinned host memory, runs one step and downloads particles,
+          fields and energies again (what a caller holding its state in host arrays pays).
+roofline  the push kernel: 56 algorithmic bytes per particle-step x particles per
+          launch / the kernel's mean duration (CUDA events around every push launch), against
+          the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_PARTICLE_STEP = 56.0       # read 8 members (32 B) + write dx,dy,dz,ux,uy,uz (24 B), float
+FALLBACK_HBM_GBS = 6650.0            # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, nargs=3, default=None, help="override the workload grid (development)")
+    ap.add_argument("--nppc", type=int, default=64)
+    ap.add_argument("--sort-interval", type=int, default=None)
+    ap.add_argument("--fp", default="strict", choices=["strict", "contract"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "slab", "replicated"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ workload
+def workload(args, free_bytes=None):
+    grid = tuple(args.grid) if args.grid else (256, 256, 256)
+    nppc = args.nppc
+    name = f"uniform thermal plasma {grid[0]}x{grid[1]}x{grid[2]} cells x {nppc} ppc (BASELINE configs[4])"
+    if free_bytes is not None and not args.grid:
+        need = grid[0] * grid[1] * grid[2] * nppc * 64 * 1.08 + 4e9      # two particle buffers + grid arrays
+        while need > free_bytes and grid[2] > 8:
+            grid = (grid[0], grid[1], grid[2] // 2)
+            need = grid[0] * grid[1] * grid[2] * nppc * 64 * 1.08 + 4e9
+            name = f"uniform thermal plasma {grid[0]}x{grid[1]}x{grid[2]} cells x {nppc} ppc (z halved to fit HBM)"
+    return grid, nppc, name
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(grid_xy, nppc, steps, warmup, min_seconds=0.0, max_steps=None):
+    """Time the reference's own CPU implementation (oracle/_ref OpenMP build of the reference
+    sources; else the scalar C restatement) on a bounded z-thin sample of the same plasma."""
+    from cabanapic_b200 import decks
+    from oracle.api import Consts as OConsts, RefLib, Restatement, State
+    nx, ny = grid_xy
+    nz = 4
+    d = decks.uniform_plasma(nx, ny, nz, nppc)
+    k, _, we = d.consts()
+    ok = OConsts(**k.to_dict())
+    p = decks.uniform_plasma_particles(d, we)
+    s = State(nx, ny, nz, 1, d.num_particles, "f32")
+    for n in p:
+        s.p[n][:] = p[n]
+    sample = f"{nx}x{ny}x{nz} cells x {nppc} ppc = {d.num_particles} particles of the same plasma, float, EM"
+    if RefLib.available("default", "f32", omp=True):
+        R = RefLib("default", "f32", omp=True).create(s, solver=0)
+        cores, kind = R.num_threads(), "reference"
+        run = lambda n: R.run(ok, n)
+    else:
+        O = Restatement("f32")
+        cores, kind = 1, "port"
+        run = lambda n: O.step(s, ok, 0, n)
+    run(max(1, warmup))
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        run(steps)
+        done += steps
+        el = time.perf_counter() - t0
+        if el >= min_seconds or (max_steps and done >= max_steps):
+            break
+    return {"value": d.num_particles * done / el, "unit": "particle-steps/s", "cores": cores, "kind": kind,
+            "sample": sample + f", {done} steps in {el:.2f} s"}, el / done * 1e3, d.num_particles
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    grid, nppc, name = workload(args)
+    # each "step" is one full time step of the bounded sample
+    cb, ms, npart = cpu_reference_run(grid[:2], nppc, args.steps, args.warmup, min_seconds=0.0,
+                                      max_steps=args.steps)
+    line = {"impl": "reference", "metric": "particle-steps/s (whole step: push+move+deposit+field advance)",
+            "value": cb["value"], "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "sample": cb["sample"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import cabanapic_b200 as cp
+    from cabanapic_b200 import decks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    free, total = torch.cuda.mem_get_info()
+    grid, nppc, name = workload(args, free_bytes=free * world)
+    nx, ny, nz = grid
+    d = decks.uniform_plasma(nx, ny, nz, nppc)
+    k, _, we = d.consts()
+    n_total = d.num_particles
+    sort_interval = args.sort_interval if args.sort_interval is not None else 1
+    fp = cp.FP_CONTRACT if args.fp == "contract" else cp.FP_STRICT
+
+    if world > 1:
+        from cabanapic_b200 import dist as cdist
+        runner = cdist.make_runner(d, k, we, rank, world, local, mode=args.mode, fp_mode=fp)
+    else:
+        runner = SingleGpu(d, k, we, local, fp)
+    runner.setup()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        runner.step(1, sort_interval)
+    barrier()
+    runner.profile(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    runner.step(args.steps, sort_interval)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = runner.device_ms()
+    clocks = sampler.stop() if rank == 0 else None
+    prof = runner.profile_result()
+    launches = runner.launches_in_timed_region()
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms, prof["push_ms"], float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, push_ms_max = t[0].item(), t[1].item(), t[2].item()
+        prof["push_ms"] = push_ms_max
+        launches = int(t[3].item())
+    elapsed_ms = max(dev_ms, 0.0) if world == 1 else wall_ms     # multi-GPU: barrier-to-barrier, max over ranks
+    value = n_total * args.steps / (elapsed_ms * 1e-3)
+
+    peak, peak_src = measured_peak()
+    push_ms_per_launch = prof["push_ms"] / args.steps
+    per_launch_particles = runner.local_particles()
+    achieved = BYTES_PER_PARTICLE_STEP * per_launch_particles / (push_ms_per_launch * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_push (push + move_p + deposit)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
+                "particles_per_launch": per_launch_particles, "ms_per_launch": push_ms_per_launch,
+                "push_only_particle_steps_per_s_per_gpu": per_launch_particles / (push_ms_per_launch * 1e-3),
+                "phase_ms_per_step": {kk: v / args.steps for kk, v in prof.items() if kk.endswith("_ms")}}
+    tr = os.path.join(ROOT, "profiles", "push_traffic.json")
+    if os.path.exists(tr):
+        try:
+            t = json.load(open(tr))
+            roofline["traffic"] = t["dram_bytes_per_particle"] * per_launch_particles
+            roofline["traffic_source"] = t.get("source")
+        except Exception:
+            pass
+
+    e2e = None
+    if not args.no_e2e and world == 1:
+        e2e = runner.e2e(args.e2e_steps, sort_interval)
+    elif world > 1:
+        e2e = runner.e2e(args.e2e_steps, sort_interval)
+        if e2e is not None:
+            t = torch.tensor([e2e["seconds"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e["value"] = n_total * e2e["steps"] / t[0].item()
+    runner.close()
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _, _ = cpu_reference_run((nx, ny), nppc, 2, 1, min_seconds=10.0, max_steps=200)
+
+    if rank == 0:
+        line = {"metric": "particle-steps/s (whole step: sort+push+move+deposit+field advance)",
+                "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": name, "particles": n_total, "cells": [nx, ny, nz], "ppc": nppc,
+                           "sort_interval": sort_interval, "fp_mode": args.fp, "deposit": "warp-aggregated",
+                           "parallelism": runner.describe(),
+                           "l2": "inputs (>= 30 GB per GPU) exceed the 126 MB L2; no flush needed"},
+                "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
+                "roofline": roofline}
+        if e2e is not None:
+            e2e.pop("seconds", None)
+            line["e2e"] = e2e
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class SingleGpu:
+    """One context on one GPU holding the whole box."""
+
+    def __init__(self, d, k, we, device, fp):
+        self.d, self.k, self.we, self.device, self.fp = d, k, we, device, fp
+        self.l0 = 0
+
+    def setup(self):
+        import cabanapic_b200 as cp
+        d = self.d
+        self.c = cp.Context(d.nx, d.ny, d.nz, 1, max_particles=d.num_particles, real=np.float32, device=self.device,
+                            fp_mode=self.fp, enable_sort=True)
+        self.c.init_uniform_plasma(0, d.num_particles, d.nx, d.ny, d.nz, d.nppc, weight=self.we)
+        self.c.upload_fields(d.initial_fields())
+        self.c.sync()
+
+    def step(self, n, sort_interval):
+        self.l0 = self.c.launch_count
+        self.c.step(self.k, n, sort_interval, False)
+        self.c.sync()
+
+    def profile(self, on):
+        self.c.enable_step_profile(on)
+
+    def profile_result(self):
+        return self.c.step_profile()
+
+    def device_ms(self):
+        return self.c.last_ms(3)
+
+    def launches_in_timed_region(self):
+        return self.c.launch_count - self.l0
+
+    def local_particles(self):
+        return self.c.num_particles
+
+    def describe(self):
+        return "1 GPU, whole domain"
+
+    def e2e(self, steps, sort_interval):
+        """Stateless steps through the C ABI with HOST buffers (pinned): upload particles and
+        fields, one step, download particles, fields and energies -- every step."""
+        import psutil
+        import torch
+        c, d = self.c, self.d
+        n = c.num_particles
+        nbytes = n * 32 + 9 * c.nc * 4
+        if psutil.virtual_memory().available < 1.6 * nbytes:
+            return {"value": None, "unit": "particle-steps/s", "h2d_bytes_per_step": nbytes,
+                    "d2h_bytes_per_step": nbytes, "note": "not enough host memory for the pinned state"}
+        names = "dx dy dz ux uy uz w".split()
+        host = {m: torch.empty(n, dtype=torch.float32, pin_memory=True).numpy() for m in names}
+        host["cell"] = torch.empty(n, dtype=torch.int32, pin_memory=True).numpy()
+        hf = torch.empty((9, c.nc), dtype=torch.float32, pin_memory=True).numpy()
+        import ctypes as C
+        L = c.L
+        ptrs = [host[m].ctypes.data_as(C.c_void_p) for m in names] + [host["cell"].ctypes.data_as(C.c_void_p)]
+        fptr = (C.c_void_p * 9)(*[hf[m].ctypes.data for m in range(9)])
+        got = C.c_int64()
+        c._ck(L.cpic_download_particles(c.h, *ptrs, n, C.byref(got)))
+        c._ck(L.cpic_download_fields(c.h, fptr))
+        en = np.zeros((1, 2))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            c._ck(L.cpic_upload_particles(c.h, *ptrs, n))
+            c._ck(L.cpic_upload_fields(c.h, fptr))
+            c._ck(L.cpic_step(c.h, C.byref(self.k), 1, sort_interval, en.ctypes.data_as(C.c_void_p)))
+            c._ck(L.cpic_download_particles(c.h, *ptrs, n, C.byref(got)))
+            c._ck(L.cpic_download_fields(c.h, fptr))
+        sec = time.perf_counter() - t0
+        return {"value": n * steps / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": nbytes,
+                "d2h_bytes_per_step": nbytes + 16, "steps": steps, "seconds": sec,
+                "what": "per step: H2D particles+fields from pinned host, cpic_step(1), D2H particles+fields+energies"}
+
+    def close(self):
+        self.c.close()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

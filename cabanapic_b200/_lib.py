@@ -120,6 +120,8 @@ def lib() -> C.CDLL:
             "cpic_set_modes": [vp, i32, i32],
             "cpic_last_ms": [vp, C.c_int, C.POINTER(dbl)],
             "cpic_launch_count": [vp, C.POINTER(i64)],
+            "cpic_enable_step_profile": [vp, i32],
+            "cpic_step_profile": [vp, C.POINTER(dbl), C.POINTER(i64)],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -137,7 +139,7 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
             "cpic_unload_accumulator_array", "cpic_advance_b", "cpic_advance_e", "cpic_uncenter_particles",
             "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_sort_particles", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
             "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
-            "cpic_last_ms", "cpic_launch_count"]
+            "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile"]
 
 
 def _p(a):
@@ -321,6 +323,16 @@ class Context:
         ms = C.c_double()
         self._ck(self.L.cpic_last_ms(self.h, what, C.byref(ms)))
         return ms.value
+
+    def enable_step_profile(self, on=True):
+        self._ck(self.L.cpic_enable_step_profile(self.h, 1 if on else 0))
+
+    def step_profile(self):
+        """ms spent in (sort, interp+clear, push, field side) over the last profiled step() call."""
+        ms = (C.c_double * 4)()
+        n = C.c_int64()
+        self._ck(self.L.cpic_step_profile(self.h, ms, C.byref(n)))
+        return {"sort_ms": ms[0], "interp_ms": ms[1], "push_ms": ms[2], "field_ms": ms[3], "steps": n.value}
 
     @property
     def launch_count(self):

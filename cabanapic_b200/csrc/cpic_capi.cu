@@ -36,7 +36,12 @@ struct CtxBase {
     cudaEvent_t ev[8]{};   // 0/1 push, 2/3 sort, 4/5 field side, 6/7 step
     bool ev_valid[4] = {false, false, false, false};
     bool want_stats = false;
-    virtual ~CtxBase() {}
+    // opt-in per-phase profile of cpic_step: 5 events per step (start, after sort, before push,
+    // after push, end) on the context's stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    long long prof_steps = 0;
+    virtual ~CtxBase() { for (auto e : prof_ev) cudaEventDestroy(e); }
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -538,17 +543,31 @@ int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_
     const double hx = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->px) : 0.5 * k->px;
     const double hy = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->py) : 0.5 * k->py;
     const double hz = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->pz) : 0.5 * k->pz;
+    const bool prof = c->prof_on;
+    if (prof) {
+        while ((long long)c->prof_ev.size() < 5 * nsteps) {
+            cudaEvent_t e;
+            if ((rc = c->cuda(cudaEventCreate(&e), "cudaEventCreate"))) return rc;
+            c->prof_ev.push_back(e);
+        }
+        c->prof_steps = nsteps;
+    }
     for (int64_t s = 0; s < nsteps && !rc; ++s) {
         // example/example.cpp:221-266, plus the optional sort of :224-228
+        if (prof) cudaEventRecord(c->prof_ev[5 * s + 0], c->stream);
         if (sort_interval > 0 && s % sort_interval == 0) rc = c->sort();
+        if (prof) cudaEventRecord(c->prof_ev[5 * s + 1], c->stream);
         if (!rc) rc = c->load_interpolator();
         if (!rc) rc = c->clear_accumulator();
+        if (prof) cudaEventRecord(c->prof_ev[5 * s + 2], c->stream);
         if (!rc) rc = c->push(*k);
+        if (prof) cudaEventRecord(c->prof_ev[5 * s + 3], c->stream);
         if (!rc) rc = c->unload_accumulator(*k);
         if (!rc) rc = c->advance_b(hx, hy, hz);
         if (!rc) rc = c->advance_e(k->px, k->py, k->pz, k->dt_eps0);
         if (!rc) rc = c->advance_b(hx, hy, hz);
         if (!rc && en) rc = c->energies_async(en + 2 * s);
+        if (prof) cudaEventRecord(c->prof_ev[5 * s + 4], c->stream);
     }
     cudaEventRecord(c->ev[7], c->stream);
     c->ev_valid[3] = true;
@@ -610,6 +629,30 @@ int cpic_set_modes(cpic_ctx* ctx, int32_t fp_mode, int32_t deposit_mode) {
 int cpic_enable_push_stats(cpic_ctx* ctx, int32_t on) {
     CTX_OR_FAIL(ctx);
     c->want_stats = on != 0;
+    return CPIC_OK;
+}
+
+int cpic_enable_step_profile(cpic_ctx* ctx, int32_t on) {
+    CTX_OR_FAIL(ctx);
+    c->prof_on = on != 0;
+    return CPIC_OK;
+}
+
+int cpic_step_profile(cpic_ctx* ctx, double ms_out[4], int64_t* steps) {
+    CTX_OR_FAIL(ctx);
+    if (!ms_out) return c->fail(CPIC_E_INVALID, "step_profile: null");
+    if (!c->prof_on || c->prof_steps == 0) return c->fail(CPIC_E_INVALID, "step_profile: no profiled cpic_step yet");
+    int rc = c->cuda(cudaStreamSynchronize(c->stream), "step_profile");
+    if (rc) return rc;
+    double sum[4] = {0, 0, 0, 0};
+    for (long long s = 0; s < c->prof_steps; ++s)
+        for (int ph = 0; ph < 4; ++ph) {
+            float f = 0.f;
+            if ((rc = c->cuda(cudaEventElapsedTime(&f, c->prof_ev[5 * s + ph], c->prof_ev[5 * s + ph + 1]), "cudaEventElapsedTime"))) return rc;
+            sum[ph] += f;
+        }
+    for (int ph = 0; ph < 4; ++ph) ms_out[ph] = sum[ph];
+    if (steps) *steps = c->prof_steps;
     return CPIC_OK;
 }
 

@@ -164,7 +164,12 @@ int  cpic_set_modes(cpic_ctx* ctx, int32_t fp_mode, int32_t deposit_mode);
 /* Device-side timing of the last call of each kind, in milliseconds (CUDA events on the
  * context's stream).  what: 0 push, 1 sort, 2 field side (interp+unload+advance), 3 step total. */
 int  cpic_last_ms(cpic_ctx* ctx, int what, double* ms);
-int  cpic_launch_count(cpic_ctx* ctx, int64_t* launches);  /* kernels launched by this ctx so far */
+int  cpic_launch_count(cpic_ctx* ctx, int64_t* launches);
+/* Opt-in per-phase timing of cpic_step with CUDA events on the context's stream.  After a
+ * profiled cpic_step, ms_out = total milliseconds over its steps spent in
+ * [0] sort, [1] interpolator load + accumulator clear, [2] push (+mover+deposit), [3] field side. */
+int  cpic_enable_step_profile(cpic_ctx* ctx, int32_t on);
+int  cpic_step_profile(cpic_ctx* ctx, double ms_out[4], int64_t* steps);  /* kernels launched by this ctx so far */
 
 #ifdef __cplusplus
 }

@@ -200,8 +200,8 @@ def test_golden_fixtures_multi_step(name, ptol, etol):
     for n in ("dx", "dy", "dz", "ux", "uy", "uz"):
         assert np.abs(p[n][same] - z["p1_" + n][same]).max() < ptol, n
     ge = z["energies"]
-    big = ge > 1e-3 * ge.max(axis=0, keepdims=True)
-    assert (np.abs(en - ge)[big] / ge[big]).max() < etol
+    # energies relative to the history's own scale (early lines sit at the noise floor)
+    assert (np.abs(en - ge).max(axis=0) / (ge.max(axis=0) + 1e-300)).max() < etol
     fscale = np.abs(z["f1"]).max(axis=1, keepdims=True) + 1e-30
     assert (np.abs(f - z["f1"]) / fscale).max() < (50 * ptol)
 
