@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcabanapic_b200.so")
+LIB_PATH = os.environ.get("CPIC_LIB") or os.path.join(HERE, "libcabanapic_b200.so")   # CPIC_LIB: developer override
 
 CONST_NAMES = "qdt_2mc cdt_dx cdt_dy cdt_dz qsp dx dy dz dt px py pz dt_eps0".split()
 PARTICLE_NAMES = "dx dy dz ux uy uz w cell".split()

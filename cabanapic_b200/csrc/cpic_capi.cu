@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -137,6 +138,11 @@ struct Ctx final : CtxBase {
         own_stream = true;
         for (auto& e : ev)
             if ((rc = cuda(cudaEventCreate(&e), "cudaEventCreate"))) return rc;
+        // developer tuning knobs (not part of the ABI)
+        if (const char* e = getenv("CPIC_PUSH_PREFETCH")) push_prefetch = atoi(e) != 0;
+        if (const char* e = getenv("CPIC_PUSH_GRID")) push_grid = atoi(e);
+        if (const char* e = getenv("CPIC_DEP_THRESH")) dep_thresh = atoi(e);
+        if (const char* e = getenv("CPIC_DEP_ROUNDS")) dep_rounds = atoi(e);
         nc_pad = (g.nc + 63) / 64 * 64;
         cap = (prm.max_particles + 63) / 64 * 64;
         if (cap < 64) cap = 64;
@@ -306,11 +312,30 @@ struct Ctx final : CtxBase {
     unsigned long long* stats_dev() override { return stats; }
 
     // ------------------------------------------------------------------ particles
+    // Persistent launch: one wave of blocks that fills the machine (SM count x resident blocks
+    // per SM), each warp grid-striding over 32-particle tiles.
+    int push_grid = 0;
+    int dep_thresh = 16, dep_rounds = 4;
+    bool push_prefetch = true;
+    template <bool FMA, int DEP, bool ST, bool PF>
+    int launch_push_k(const PushArgs<R>& a) {
+        auto kern = k_push<R, FMA, DEP, ST, PF>;
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PUSH_WARPS * 32, 0);
+        if (per_sm < 1) per_sm = 1;
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device);
+        long long blocks = (long long)sms * per_sm;
+        const long long need = (np + PUSH_WARPS * 32 - 1) / (PUSH_WARPS * 32);
+        if (blocks > need) blocks = need;
+        if (push_grid > 0) blocks = std::min<long long>(push_grid, need);
+        kern<<<(unsigned)blocks, PUSH_WARPS * 32, 0, stream>>>(a);
+        return check_launch("k_push");
+    }
     template <bool FMA, int DEP>
     int launch_push(const PushArgs<R>& a) {
-        if (want_stats) k_push<R, FMA, DEP, true><<<blocks_for(np), 256, 0, stream>>>(a);
-        else k_push<R, FMA, DEP, false><<<blocks_for(np), 256, 0, stream>>>(a);
-        return check_launch("k_push");
+        if (want_stats) return push_prefetch ? launch_push_k<FMA, DEP, true, true>(a) : launch_push_k<FMA, DEP, true, false>(a);
+        return push_prefetch ? launch_push_k<FMA, DEP, false, true>(a) : launch_push_k<FMA, DEP, false, false>(a);
     }
     int push(const cpic_consts& k) override {
         if (np == 0) return CPIC_OK;
@@ -320,6 +345,7 @@ struct Ctx final : CtxBase {
         a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.ng = g.ng; a.gx = g.gx; a.gy = g.gy;
         a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC;
         a.stats = stats;
+        a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
         cudaEventRecord(ev[0], stream);
         int dep = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;

@@ -35,6 +35,8 @@ struct PushArgs {
     R qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
     int nx, ny, nz, ng, gx, gy;
     int periodic;
+    int dep_thresh;   // mixed warps: runs at least this long are warp-reduced, shorter ones use direct atomics
+    int dep_rounds;   // mixed warps: at most this many peel rounds before falling back to direct atomics
     unsigned long long* stats;  // optional: [0] movers [1] crossings [2..7] wraps per face
 };
 
@@ -133,7 +135,8 @@ __device__ __forceinline__ R warp_transpose_sum12(const R (&a)[12], int lane) {
 
 // First-streak deposit; must be called by all 32 lanes of the warp (converged).
 template <class R, int DEPOSIT>
-__device__ __forceinline__ void deposit_first(R* __restrict__ acc, bool valid, int ii, const R (&a)[12], int lane) {
+__device__ __forceinline__ void deposit_first(R* __restrict__ acc, bool valid, int ii, const R (&a)[12], int lane,
+                                              int thresh, int rounds) {
     if constexpr (DEPOSIT == 1) {
         if (valid) row_add_scalar(acc + (long long)ii * 12, a);
     } else if constexpr (DEPOSIT == 2) {
@@ -147,35 +150,32 @@ __device__ __forceinline__ void deposit_first(R* __restrict__ acc, bool valid, i
         unsigned same = __ballot_sync(full, valid && ii == c0);
         const int e = ((lane >> 1) & 7) | ((lane & 16) >> 1);  // entry this lane ends up holding
         if (same == vmask) {  // the common case for cell-sorted particles: one row per warp
-            R z[12];
-#pragma unroll
-            for (int j = 0; j < 12; ++j) z[j] = valid ? a[j] : R(0);
-            const R tot = warp_transpose_sum12(z, lane);
+            // (lanes that do not contribute pass all-zero currents, so no masking is needed)
+            const R tot = warp_transpose_sum12(a, lane);
             if (!(lane & 1) && e < 12) atomicAdd(acc + (long long)c0 * 12 + e, tot);
             return;
         }
-        // Mixed warp: peel off one cell at a time while groups are big enough to be worth a
-        // warp reduction; the remaining stragglers update their rows directly.
+        // Mixed warp: peel off one cell at a time (sorted particles give 2-3 runs per warp).  A
+        // run that is long enough is summed with the warp transpose; short runs and whatever is
+        // left after four rounds (unsorted input) update their rows directly.
         unsigned todo = vmask;
         bool mine_done = !valid;
-        int guard = 0;
-        while (todo) {
+        for (int round = 0; todo && round < rounds; ++round) {
             const int ld = __ffs(todo) - 1;
             const int c = __shfl_sync(full, ii, ld);
             const bool mine = !mine_done && ii == c;
             const unsigned grp = __ballot_sync(full, mine);
-            if (__popc(grp) >= 6 && guard < 4) {
+            if (__popc(grp) >= thresh) {
                 R z[12];
 #pragma unroll
                 for (int j = 0; j < 12; ++j) z[j] = mine ? a[j] : R(0);
                 const R tot = warp_transpose_sum12(z, lane);
                 if (!(lane & 1) && e < 12) atomicAdd(acc + (long long)c * 12 + e, tot);
-                if (mine) mine_done = true;
-                todo &= ~grp;
-                ++guard;
-            } else {
-                break;
+            } else if (mine) {
+                row_add_vec(acc + (long long)ii * 12, a);
             }
+            if (mine) mine_done = true;
+            todo &= ~grp;
         }
         if (!mine_done) row_add_vec(acc + (long long)ii * 12, a);
     }
@@ -266,105 +266,203 @@ __device__ __forceinline__ void load_record(const R* __restrict__ ip, int ii, R 
 }
 
 // ---------------------------------------------------------------------------------------
+// The push kernel: persistent and warp-autonomous.
+//
+// The grid is sized to fill the machine once (SMs x resident blocks); every warp walks the
+// particle store in 32-particle tiles with a grid stride, so consecutive warps touch
+// consecutive 128-byte lines of each member array and no block barrier or block launch is on
+// the per-tile path.  Per tile:
+//   1. each lane advances one particle (gather, Boris, displacement);
+//   2. particles that stay in their cell (~87 %) store their new position and put their 12
+//      currents into the warp-aggregated row update (deposit_first);
+//   3. particles that leave their cell are NOT moved yet: the lane appends a compact mover
+//      record to the warp's private shared-memory list -- the in-kernel form of VPIC's
+//      particle_mover_t list that the reference kept only in comments (src/push.h:271-291,
+//      src/types.h:175-179).  Whenever the list holds a full warp's worth it is drained
+//      densely, one mover per lane, so the divergent cell-crossing loop (IEEE divides, index
+//      arithmetic, 1-4 streaks) runs with 32 active lanes instead of 3-4.
+// The next tile's eight member loads are issued before the current tile's arithmetic
+// (PREFETCH) so DRAM latency overlaps compute within the warp, not just across warps.
+#ifndef PUSH_MIN_BLOCKS
+#define PUSH_MIN_BLOCKS 4
+#endif
+constexpr int PUSH_WARPS = 8;          // warps per block
+constexpr int MOVER_CAP = 64;          // per-warp list capacity (drained at >= 32)
+
+template <class R>
+struct WarpMoverList {
+    R x[MOVER_CAP], y[MOVER_CAP], z[MOVER_CAP], rx[MOVER_CAP], ry[MOVER_CAP], rz[MOVER_CAP], q[MOVER_CAP];
+    int cell[MOVER_CAP];
+    unsigned idx[MOVER_CAP];   // global particle index (< 2^31)
+};
+
+// Drain list entries [first, first+32) (lanes beyond `count` idle).  Reference: move_p,
+// src/move_p.h:93-371 -- streak, deposit into the current cell, then either stop (end of
+// track) or cross the face into the neighbour and continue.
 template <class R, bool FMA, int DEPOSIT, bool STATS>
-__global__ void __launch_bounds__(256) k_push(PushArgs<R> a) {
-    const long long n = blockIdx.x * 256LL + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool valid = n < a.np;
-    const R one = R(1.), one_third = R(1. / 3.), two_fifteenths = R(2. / 15.);
-
-    int ii = 0;
-    bool mover = false;
-    int axis = 3;
-    R x = 0, y = 0, z = 0;        // stored position (updated as the mover advances)
-    R rx = 0, ry = 0, rz = 0;     // remaining half displacement (mover only)
-    R q = 0, dirv = 0;
-    R cur[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) cur[j] = R(0);
-
-    if (valid) {
-        ii = a.p.cell[n];
-        R f[IpStride<R>::value];
-        load_record(a.ip, ii, f);
-        x = a.p.dx[n]; y = a.p.dy[n]; z = a.p.dz[n];
-        R ux = a.p.ux[n], uy = a.p.uy[n], uz = a.p.uz[n];
-        q = a.p.w[n] * a.qsp;
-
-        // src/push.h:124-138 -- trilinear E, linear B at the particle
-        const R hax = a.qdt_2mc * madd<FMA>(z, madd<FMA>(y, f[I_D2EXDYDZ], f[I_DEXDZ]), madd<FMA>(y, f[I_DEXDY], f[I_EX]));
-        const R hay = a.qdt_2mc * madd<FMA>(x, madd<FMA>(z, f[I_D2EYDZDX], f[I_DEYDX]), madd<FMA>(z, f[I_DEYDZ], f[I_EY]));
-        const R haz = a.qdt_2mc * madd<FMA>(y, madd<FMA>(x, f[I_D2EZDXDY], f[I_DEZDY]), madd<FMA>(x, f[I_DEZDX], f[I_EZ]));
-        const R cbx = madd<FMA>(x, f[I_DCBXDX], f[I_CBX]);
-        const R cby = madd<FMA>(y, f[I_DCBYDY], f[I_CBY]);
-        const R cbz = madd<FMA>(z, f[I_DCBZDZ], f[I_CBZ]);
-
-        ux += hax; uy += hay; uz += haz;                                  // half E kick, :144-146
-        // :148 -- sqrtf even when real_t is double (argument rounds to float first)
-        R v0 = a.qdt_2mc / (R)sqrtf((float)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));
-        R v1 = madd<FMA>(cbx, cbx, madd<FMA>(cby, cby, cbz * cbz));
-        R v2 = (v0 * v0) * v1;
-        R v3 = v0 * madd<FMA>(v2, madd<FMA>(v2, two_fifteenths, one_third), one);
-        R v4 = v3 / madd<FMA>(v1, v3 * v3, one);
-        v4 += v4;
-        v0 = madd<FMA>(v3, mdiff<FMA>(uy, cbz, uz, cby), ux);              // Boris u', :155-157
-        v1 = madd<FMA>(v3, mdiff<FMA>(uz, cbx, ux, cbz), uy);
-        v2 = madd<FMA>(v3, mdiff<FMA>(ux, cby, uy, cbx), uz);
-        ux = madd<FMA>(v4, mdiff<FMA>(v1, cbz, v2, cby), ux);              // rotation, :158-160
-        uy = madd<FMA>(v4, mdiff<FMA>(v2, cbx, v0, cbz), uy);
-        uz = madd<FMA>(v4, mdiff<FMA>(v0, cby, v1, cbx), uz);
-        ux += hax; uy += hay; uz += haz;                                  // second half kick
-        a.p.ux[n] = ux; a.p.uy[n] = uy; a.p.uz[n] = uz;                   // :165-167
-
-        v0 = one / (R)sqrtf((float)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));  // :169
-        ux *= a.cdt_dx; uy *= a.cdt_dy; uz *= a.cdt_dz;                   // this order, :171-176
-        ux *= v0; uy *= v0; uz *= v0;
-        v0 = x + ux; v1 = y + uy; v2 = z + uz;                            // streak midpoint
-        v3 = v0 + ux; v4 = v1 + uy;                                       // new position
-        const R v5n = v2 + uz;
-
-        if (v3 <= one && v4 <= one && v5n <= one && -v3 <= one && -v4 <= one && -v5n <= one) {  // :187
-            a.p.dx[n] = v3; a.p.dy[n] = v4; a.p.dz[n] = v5n;
-            const R v5 = q * ux * uy * uz * one_third;                    // :203
-            streak_currents<FMA>(q, ux, uy, uz, v0, v1, v2, v5, cur);
-        } else {
-            mover = true;
-            rx = ux; ry = uy; rz = uz;                                    // local_pm, :261-263
-            R sx, sy, sz, mx, my, mz, v5;
-            axis = mover_streak(x, y, z, rx, ry, rz, q, sx, sy, sz, mx, my, mz, v5, dirv);
-            streak_currents<FMA>(q, sx, sy, sz, mx, my, mz, v5, cur);
-        }
-    }
-
-    // first streak of every particle lands in the particle's current cell
-    deposit_first<R, DEPOSIT>(a.acc, valid, ii, cur, lane);
-
-    unsigned long long n_cross = 0, n_wrap[6] = {0, 0, 0, 0, 0, 0};
-    if (mover) {
-        while (axis != 3) {
+__device__ __forceinline__ void drain_movers(const PushArgs<R>& a, WarpMoverList<R>& ml, int first, int count,
+                                             int lane, unsigned long long& n_cross, unsigned long long (&n_wrap)[6]) {
+    const int m = first + lane;
+    if (lane < count) {
+        R px = ml.x[m], py = ml.y[m], pz = ml.z[m];
+        R dx = ml.rx[m], dy = ml.ry[m], dz = ml.rz[m];
+        const R qq = ml.q[m];
+        int c = ml.cell[m];
+        const int c_in = c;
+        for (;;) {
+            R sx, sy, sz, mx, my, mz, v5, dirv;
+            const int axis = mover_streak(px, py, pz, dx, dy, dz, qq, sx, sy, sz, mx, my, mz, v5, dirv);
+            R jc[12];
+            streak_currents<FMA>(qq, sx, sy, sz, mx, my, mz, v5, jc);
+            if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)c * 12, jc);
+            else row_add_vec(a.acc + (long long)c * 12, jc);
+            if (axis == 3) break;
             // snap onto the face, move to the neighbour, re-enter from its other side
-            const int code = cross_face(ii, axis, dirv, a);
-            if (axis == 0) x = -dirv;
-            if (axis == 1) y = -dirv;
-            if (axis == 2) z = -dirv;
+            const int code = cross_face(c, axis, dirv, a);
+            if (axis == 0) px = -dirv;
+            if (axis == 1) py = -dirv;
+            if (axis == 2) pz = -dirv;
             if (STATS) {
                 ++n_cross;
                 if (code >> 4) ++n_wrap[(code >> 4) - 8];
             }
-            R sx, sy, sz, mx, my, mz, v5;
-            axis = mover_streak(x, y, z, rx, ry, rz, q, sx, sy, sz, mx, my, mz, v5, dirv);
-            streak_currents<FMA>(q, sx, sy, sz, mx, my, mz, v5, cur);
-            if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)ii * 12, cur);
-            else row_add_vec(a.acc + (long long)ii * 12, cur);
         }
-        a.p.dx[n] = x; a.p.dy[n] = y; a.p.dz[n] = z;
-        a.p.cell[n] = ii;
+        const long long pn = ml.idx[m];
+        a.p.dx[pn] = px; a.p.dy[pn] = py; a.p.dz[pn] = pz;
+        if (c != c_in) a.p.cell[pn] = c;
     }
+    __syncwarp();
+}
+
+template <class R, bool FMA, int DEPOSIT, bool STATS, bool PREFETCH>
+__global__ void __launch_bounds__(PUSH_WARPS * 32, (sizeof(R) == 4 ? PUSH_MIN_BLOCKS : (PUSH_MIN_BLOCKS + 1) / 2))
+k_push(PushArgs<R> a) {
+    __shared__ WarpMoverList<R> lists[PUSH_WARPS];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    WarpMoverList<R>& ml = lists[warp];
+    const long long ntiles = (a.np + 31) / 32;
+    const long long stride = (long long)gridDim.x * PUSH_WARPS;
+    const R one = R(1.), one_third = R(1. / 3.), two_fifteenths = R(2. / 15.);
+    int nlist = 0;                                    // movers waiting in this warp's list
+    unsigned long long n_mov = 0, n_cross = 0, n_wrap[6] = {0, 0, 0, 0, 0, 0};
+
+    long long tile = (long long)blockIdx.x * PUSH_WARPS + warp;
+    // registers for the tile being processed (+ the next one when prefetching)
+    int ii = 0;
+    R x = 0, y = 0, z = 0, ux = 0, uy = 0, uz = 0, w = 0;
+    if (tile < ntiles) {
+        const long long n = tile * 32 + lane;
+        if (n < a.np) {
+            ii = a.p.cell[n]; x = a.p.dx[n]; y = a.p.dy[n]; z = a.p.dz[n];
+            ux = a.p.ux[n]; uy = a.p.uy[n]; uz = a.p.uz[n]; w = a.p.w[n];
+        }
+    }
+    for (; tile < ntiles; tile += stride) {
+        const long long n = tile * 32 + lane;
+        const bool valid = n < a.np;
+        // next tile's members: issue the loads now, consume them next iteration
+        int ii_n = 0;
+        R x_n = 0, y_n = 0, z_n = 0, ux_n = 0, uy_n = 0, uz_n = 0, w_n = 0;
+        if (PREFETCH) {
+            const long long nn = (tile + stride) * 32 + lane;
+            if (nn < a.np) {
+                ii_n = a.p.cell[nn]; x_n = a.p.dx[nn]; y_n = a.p.dy[nn]; z_n = a.p.dz[nn];
+                ux_n = a.p.ux[nn]; uy_n = a.p.uy[nn]; uz_n = a.p.uz[nn]; w_n = a.p.w[nn];
+            }
+        }
+
+        bool mover = false, stay = false;
+        R rx = 0, ry = 0, rz = 0, q = 0;
+        R cur[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) cur[j] = R(0);
+
+        if (valid) {
+            R f[IpStride<R>::value];
+            load_record(a.ip, ii, f);
+            q = w * a.qsp;
+            // src/push.h:124-138 -- trilinear E, linear B at the particle
+            const R hax = a.qdt_2mc * madd<FMA>(z, madd<FMA>(y, f[I_D2EXDYDZ], f[I_DEXDZ]), madd<FMA>(y, f[I_DEXDY], f[I_EX]));
+            const R hay = a.qdt_2mc * madd<FMA>(x, madd<FMA>(z, f[I_D2EYDZDX], f[I_DEYDX]), madd<FMA>(z, f[I_DEYDZ], f[I_EY]));
+            const R haz = a.qdt_2mc * madd<FMA>(y, madd<FMA>(x, f[I_D2EZDXDY], f[I_DEZDY]), madd<FMA>(x, f[I_DEZDX], f[I_EZ]));
+            const R cbx = madd<FMA>(x, f[I_DCBXDX], f[I_CBX]);
+            const R cby = madd<FMA>(y, f[I_DCBYDY], f[I_CBY]);
+            const R cbz = madd<FMA>(z, f[I_DCBZDZ], f[I_CBZ]);
+
+            ux += hax; uy += hay; uz += haz;                                  // half E kick, :144-146
+            // :148 -- sqrtf even when real_t is double (argument rounds to float first)
+            R v0 = a.qdt_2mc / (R)sqrtf((float)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));
+            R v1 = madd<FMA>(cbx, cbx, madd<FMA>(cby, cby, cbz * cbz));
+            R v2 = (v0 * v0) * v1;
+            R v3 = v0 * madd<FMA>(v2, madd<FMA>(v2, two_fifteenths, one_third), one);
+            R v4 = v3 / madd<FMA>(v1, v3 * v3, one);
+            v4 += v4;
+            v0 = madd<FMA>(v3, mdiff<FMA>(uy, cbz, uz, cby), ux);              // Boris u', :155-157
+            v1 = madd<FMA>(v3, mdiff<FMA>(uz, cbx, ux, cbz), uy);
+            v2 = madd<FMA>(v3, mdiff<FMA>(ux, cby, uy, cbx), uz);
+            ux = madd<FMA>(v4, mdiff<FMA>(v1, cbz, v2, cby), ux);              // rotation, :158-160
+            uy = madd<FMA>(v4, mdiff<FMA>(v2, cbx, v0, cbz), uy);
+            uz = madd<FMA>(v4, mdiff<FMA>(v0, cby, v1, cbx), uz);
+            ux += hax; uy += hay; uz += haz;                                  // second half kick
+            a.p.ux[n] = ux; a.p.uy[n] = uy; a.p.uz[n] = uz;                   // :165-167
+
+            v0 = one / (R)sqrtf((float)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));  // :169
+            ux *= a.cdt_dx; uy *= a.cdt_dy; uz *= a.cdt_dz;                   // this order, :171-176
+            ux *= v0; uy *= v0; uz *= v0;
+            v0 = x + ux; v1 = y + uy; v2 = z + uz;                            // streak midpoint
+            v3 = v0 + ux; v4 = v1 + uy;                                       // new position
+            const R v5n = v2 + uz;
+
+            if (v3 <= one && v4 <= one && v5n <= one && -v3 <= one && -v4 <= one && -v5n <= one) {  // :187
+                stay = true;
+                a.p.dx[n] = v3; a.p.dy[n] = v4; a.p.dz[n] = v5n;
+                const R v5 = q * ux * uy * uz * one_third;                    // :203
+                streak_currents<FMA>(q, ux, uy, uz, v0, v1, v2, v5, cur);
+            } else {
+                mover = true;
+                rx = ux; ry = uy; rz = uz;                                    // local_pm, :261-263
+            }
+        }
+
+        // in-cell particles: one streak into the particle's own cell
+        deposit_first<R, DEPOSIT>(a.acc, stay, ii, cur, lane, a.dep_thresh, a.dep_rounds);
+
+        // movers: append to the warp's list (warp-synchronous, no atomics)
+        const unsigned mm = __ballot_sync(0xffffffffu, mover);
+        if (mm) {
+            if (mover) {
+                const int m = nlist + __popc(mm & ((1u << lane) - 1u));
+                ml.x[m] = x; ml.y[m] = y; ml.z[m] = z;
+                ml.rx[m] = rx; ml.ry[m] = ry; ml.rz[m] = rz;
+                ml.q[m] = q; ml.cell[m] = ii; ml.idx[m] = (unsigned)n;
+            }
+            nlist += __popc(mm);
+            if (STATS) n_mov += mover ? 1 : 0;
+            __syncwarp();
+            if (nlist >= 32) {       // drain the newest 32 (keeps the rest at the front)
+                nlist -= 32;
+                drain_movers<R, FMA, DEPOSIT, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap);
+            }
+        }
+
+        if (PREFETCH) {
+            ii = ii_n; x = x_n; y = y_n; z = z_n; ux = ux_n; uy = uy_n; uz = uz_n; w = w_n;
+        } else {
+            const long long nn = (tile + stride) * 32 + lane;
+            if (nn < a.np) {
+                ii = a.p.cell[nn]; x = a.p.dx[nn]; y = a.p.dy[nn]; z = a.p.dz[nn];
+                ux = a.p.ux[nn]; uy = a.p.uy[nn]; uz = a.p.uz[nn]; w = a.p.w[nn];
+            }
+        }
+    }
+    if (nlist > 0) drain_movers<R, FMA, DEPOSIT, STATS>(a, ml, 0, nlist, lane, n_cross, n_wrap);
 
     if (STATS) {
+        __syncwarp();
         const unsigned full = 0xffffffffu;
         unsigned long long v[8];
-        v[0] = mover ? 1ull : 0ull; v[1] = n_cross;
+        v[0] = n_mov; v[1] = n_cross;
 #pragma unroll
         for (int k = 0; k < 6; ++k) v[2 + k] = n_wrap[k];
 #pragma unroll

@@ -11,13 +11,31 @@ namespace cpic {
 
 // Also validates cell indices (the reference has no check: decks/2stream-short.cxx at HEAD
 // overruns the grid silently).  bad[0] counts out-of-range cells.
+// Length of the run of equal keys that starts at this lane (0 for lanes that do not start a
+// run).  Particles are nearly cell-sorted, so a warp usually holds 1-3 runs: one atomic per
+// run instead of one per particle.  Keys of invalid (tail) lanes must be unique negatives.
+__device__ __forceinline__ int run_length_at_head(int key, int lane, int& rank_in_run, int& head_lane) {
+    const unsigned full = 0xffffffffu;
+    const int prev = __shfl_up_sync(full, key, 1);
+    const bool head = (lane == 0) || (key != prev);
+    const unsigned heads = __ballot_sync(full, head);
+    const unsigned below = heads & ((2u << lane) - 1u);          // heads at or below this lane
+    head_lane = 31 - __clz(below);
+    rank_in_run = lane - head_lane;
+    const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+    const int next = above ? (lane + __ffs(above)) : 32;
+    return head ? (next - lane) : 0;
+}
+
 __global__ void __launch_bounds__(256) k_cell_histogram(const int* __restrict__ cell, long long np, long long nc,
                                                         unsigned* __restrict__ count, unsigned* __restrict__ bad) {
     const long long n = blockIdx.x * 256LL + threadIdx.x;
-    if (n >= np) return;
-    const int c = cell[n];
-    if (c < 0 || c >= nc) { atomicAdd(bad, 1u); return; }
-    atomicAdd(count + c, 1u);
+    const int lane = threadIdx.x & 31;
+    int c = (n < np) ? cell[n] : -1 - lane;
+    if (n < np && (c < 0 || c >= nc)) { atomicAdd(bad, 1u); c = -1 - lane; }
+    int rank, head_lane;
+    const int len = run_length_at_head(c, lane, rank, head_lane);
+    if (len > 0 && c >= 0) atomicAdd(count + c, (unsigned)len);
 }
 
 __global__ void __launch_bounds__(256) k_check_cells(const int* __restrict__ cell, long long np, long long nc,
@@ -71,8 +89,8 @@ __global__ void __launch_bounds__(256) k_scan_add(unsigned* __restrict__ out, lo
         if (base + k < n) out[base + k] += add;
 }
 
-// Scatter: slot = cursor[cell]++ (cursor starts at the scanned offsets).  Lanes of a warp
-// that share a cell claim a contiguous block with one atomic, keeping their relative order.
+// Scatter: slot = cursor[cell]++ (cursor starts at the scanned offsets).  Each run of equal
+// cells inside a warp claims a contiguous block with one atomic, keeping its relative order.
 template <class R>
 __global__ void __launch_bounds__(256) k_sort_scatter(Particles<R> src, Particles<R> dst, long long np,
                                                       unsigned* __restrict__ cursor) {
@@ -80,12 +98,11 @@ __global__ void __launch_bounds__(256) k_sort_scatter(Particles<R> src, Particle
     const int lane = threadIdx.x & 31;
     const bool valid = n < np;
     const int c = valid ? src.cell[n] : -1 - lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    const int leader = __ffs(peers) - 1;
-    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int rank, head_lane;
+    const int len = run_length_at_head(c, lane, rank, head_lane);
     unsigned base = 0;
-    if (valid && lane == leader) base = atomicAdd(cursor + c, (unsigned)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
+    if (len > 0 && valid) base = atomicAdd(cursor + c, (unsigned)len);
+    base = __shfl_sync(0xffffffffu, base, head_lane);
     if (!valid) return;
     const long long d = (long long)base + rank;
     dst.dx[d] = src.dx[n]; dst.dy[d] = src.dy[n]; dst.dz[d] = src.dz[n];

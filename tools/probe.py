@@ -42,22 +42,22 @@ def main():
     c.set_modes(cp.FP_STRICT, 3)
     # drift without sorting: how quickly does the warp-uniform fast path decay?
     c.sort_particles()
-    for s in range(6):
+    for s in range(24):
         c.load_interpolator_array(); c.clear_accumulator_array(); c.push(k); c.sync()
         print(f"push step {s} since sort: {c.last_ms(0):8.3f} ms", flush=True)
         out[f"push_since_sort_{s}_ms"] = c.last_ms(0)
     c.sort_particles(); c.sync()
-    print(f"sort (drifted 6 steps): {c.last_ms(1):8.3f} ms")
-    out["sort_drift6_ms"] = c.last_ms(1)
+    print(f"sort (drifted 24 steps): {c.last_ms(1):8.3f} ms")
+    out["sort_drift24_ms"] = c.last_ms(1)
     c.sort_particles(); c.sync()
     print(f"sort (already sorted) : {c.last_ms(1):8.3f} ms")
     out["sort_sorted_ms"] = c.last_ms(1)
     # whole fused steps, sort every step
-    for si in (1, 2, 4, 0):
+    for si in (1, 4, 8, 16, 0):
         c.sort_particles()
         c.step(k, 2, si, False); c.sync()
-        c.step(k, 8, si, False); c.sync()
-        ms = c.last_ms(3) / 8
+        c.step(k, 32, si, False); c.sync()
+        ms = c.last_ms(3) / 32
         print(f"fused step sort_interval={si}: {ms:8.3f} ms/step  {n / ms / 1e6:8.1f} Mp/ms  {56 * n / ms / 1e6:8.1f} GB/s")
         out[f"step_sort{si}_ms"] = ms
     os.makedirs("gpurun_out", exist_ok=True)
