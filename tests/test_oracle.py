@@ -134,3 +134,33 @@ def test_restatement_reproduces_golden_fixtures(name):
         assert np.array_equal(s.p[n], z["p1_" + n]), n
     assert np.array_equal(s.f, z["f1"])
     assert np.array_equal(en, z["energies"])
+
+
+def test_float_history_summation_order_sensitivity():
+    """Justifies the float tolerance used for the GPU (tests/test_gpu_parity.py): merely
+    permuting the particle order in the SERIAL oracle -- the only change is the order in which
+    the float accumulator sums the same deposits -- moves the early E-energy minima of the
+    2stream-em history by > 0.3 % relative, while the history stays within 0.5 % of the local
+    oscillation envelope before saturation.  Inside the reference's comparison window (chaotic,
+    post-saturation) this permutation lands at 13.7 % -- i.e. the reference's own 10 % float
+    criterion does not survive a reordering of its own sums (its CI only runs double) -- so
+    float histories from a different summation order are held to 25 % there."""
+    from oracle.api import State
+    z = np.load(os.path.join(GOLDEN, "state_2stream-em_f32.npz"))
+    gold = np.load(os.path.join(GOLDEN, "energies_gold_2stream-em.npz"))
+    lines, g, env = gold["lines"], gold["f32"], gold["env_f32"]
+    nx, ny, nz, ng, _, solver = [int(v) for v in z["meta"]]
+    k = Consts(**{n: float(v) for n, v in zip("qdt_2mc cdt_dx cdt_dy cdt_dz qsp dx dy dz dt px py pz dt_eps0".split(),
+                                              z["consts"])})
+    perm = np.random.default_rng(3).permutation(len(z["p0_cell"]))
+    s = State(nx, ny, nz, ng, len(perm), "f32")
+    for n in PARTICLE_NAMES:
+        s.p[n][:] = z["p0_" + n][perm]
+    s.f[:] = z["f0"]
+    en = Restatement("f32").step(s, k, solver, 6000, energies=True)[lines]
+    rel = np.abs(en - g) / np.minimum(en, g)
+    erel = np.abs(en - g) / env
+    window = (lines >= 3581) & (lines < 4881)
+    assert rel[lines < 3581].max() > 3e-3          # order alone already breaks a tight min-relative bound
+    assert erel[lines < 3581].max() < 5e-3
+    assert 0.10 < rel[window].max() < 0.25
