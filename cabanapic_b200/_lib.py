@@ -118,6 +118,11 @@ def lib() -> C.CDLL:
             "cpic_set_stream": [vp, vp],
             "cpic_set_num_particles": [vp, i64],
             "cpic_set_modes": [vp, i32, i32],
+            "cpic_set_axis_periodic": [vp, i32, i32, i32],
+            "cpic_advance_b_stencil": [vp, dbl, dbl, dbl],
+            "cpic_advance_e_stencil": [vp, dbl, dbl, dbl, dbl],
+            "cpic_extract_z_leavers": [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i64), i32, i32],
+            "cpic_append_particles_device": [vp, vp, i64, i64],
             "cpic_last_ms": [vp, C.c_int, C.POINTER(dbl)],
             "cpic_launch_count": [vp, C.POINTER(i64)],
             "cpic_enable_step_profile": [vp, i32],
@@ -139,6 +144,7 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
             "cpic_unload_accumulator_array", "cpic_advance_b", "cpic_advance_e", "cpic_uncenter_particles",
             "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_sort_particles", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
             "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
+            "cpic_set_axis_periodic", "cpic_advance_b_stencil", "cpic_advance_e_stencil", "cpic_extract_z_leavers", "cpic_append_particles_device",
             "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile"]
 
 
@@ -310,6 +316,25 @@ class Context:
 
     def set_num_particles(self, n):
         self._ck(self.L.cpic_set_num_particles(self.h, n))
+
+    def set_axis_periodic(self, px, py, pz):
+        self._ck(self.L.cpic_set_axis_periodic(self.h, int(px), int(py), int(pz)))
+
+    def advance_b_stencil(self, px, py, pz):
+        self._ck(self.L.cpic_advance_b_stencil(self.h, px, py, pz))
+
+    def advance_e_stencil(self, px, py, pz, dt_eps0):
+        self._ck(self.L.cpic_advance_e_stencil(self.h, px, py, pz, dt_eps0))
+
+    def extract_z_leavers(self, lo_ptr, hi_ptr, capacity, rebase_lo, rebase_hi):
+        """Device pointers in, (n_lo, n_hi) out; see include/cabanapic_b200.h."""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.L.cpic_extract_z_leavers(self.h, C.c_void_p(lo_ptr), C.c_void_p(hi_ptr), capacity, C.byref(a),
+                                               C.byref(b), rebase_lo, rebase_hi))
+        return a.value, b.value
+
+    def append_particles_device(self, ptr, capacity, n):
+        self._ck(self.L.cpic_append_particles_device(self.h, C.c_void_p(ptr), capacity, n))
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.cpic_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

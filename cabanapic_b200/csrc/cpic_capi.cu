@@ -19,6 +19,7 @@
 #include "cpic_particles.cuh"
 #include "cpic_sort.cuh"
 #include "cpic_init.cuh"
+#include "cpic_migrate.cuh"
 
 using namespace cpic;
 
@@ -81,6 +82,10 @@ struct CtxBase {
     virtual int sort() = 0;
     virtual int init_uniform(const UniformPlasmaArgs& a) = 0;
     virtual int device_ptr(int which, void** ptr, int64_t* count, int64_t* stride) = 0;
+    virtual int fold_phase(int phase) = 0;
+    virtual int stencil_only(int which, double px, double py, double pz, double dt_eps0) = 0;
+    virtual int extract_z(void* lo, void* hi, long long cap, long long* n_lo, long long* n_hi, int rebase_lo, int rebase_hi) = 0;
+    virtual int append_device(const void* buf, long long cap, long long n) = 0;
     virtual double* energy_scratch() = 0;
     virtual unsigned long long* stats_dev() = 0;
 };
@@ -112,7 +117,7 @@ struct Ctx final : CtxBase {
             cudaSetDevice(prm.device);
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(fields); cudaFree(interp); cudaFree(acc);
-            cudaFree(cell_count); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats);
+            cudaFree(cell_count); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists);
             if (own_stream && stream) cudaStreamDestroy(stream);
         }
     }
@@ -273,11 +278,86 @@ struct Ctx final : CtxBase {
         k_ghost_fold<R, 1><<<dim3(blocks_for(m1), 3), 256, 0, stream>>>(f.c[F_JFX], f.c[F_JFY], f.c[F_JFZ], g);
         return check_launch("k_ghost_fold<1>");
     }
+    int fold_phase(int phase) override {
+        Fields<R> f = F();
+        const long long m0 = std::max({(long long)g.nx * (g.nz + 1), (long long)g.ny * (g.nx + 1), (long long)g.nz * (g.ny + 1)});
+        const long long m1 = std::max({(long long)g.nx * (g.ny + 1), (long long)g.ny * (g.nz + 1), (long long)g.nz * (g.nx + 1)});
+        if (phase == 0) k_ghost_fold<R, 0><<<dim3(blocks_for(m0), 3), 256, 0, stream>>>(f.c[F_JFX], f.c[F_JFY], f.c[F_JFZ], g);
+        else k_ghost_fold<R, 1><<<dim3(blocks_for(m1), 3), 256, 0, stream>>>(f.c[F_JFX], f.c[F_JFY], f.c[F_JFZ], g);
+        return check_launch("k_ghost_fold");
+    }
+    // ------------------------------------------------------------------ slab migration
+    unsigned* mig_counters = nullptr;   // 8 counters
+    unsigned* mig_lists = nullptr;      // 2 * mig_cap indices: [0,mig_cap) holes, [mig_cap,2*mig_cap) donors
+    long long mig_cap = 0;
+    int extract_z(void* lo, void* hi, long long cap_send, long long* n_lo, long long* n_hi, int rebase_lo, int rebase_hi) override {
+        int rc;
+        if (cap_send < 1) return fail(CPIC_E_INVALID, "extract_z_leavers: capacity must be positive");
+        if (!mig_counters && (rc = cuda(cudaMalloc(&mig_counters, 8 * sizeof(unsigned)), "cudaMalloc"))) return rc;
+        if (mig_cap < 2 * cap_send) {      // up to n_lo + n_hi <= 2*cap_send holes, and as many donors
+            cudaFree(mig_lists); mig_lists = nullptr;
+            if ((rc = cuda(cudaMalloc(&mig_lists, (size_t)4 * cap_send * sizeof(unsigned)), "cudaMalloc(migration lists)"))) return rc;
+            mig_cap = 2 * cap_send;
+        }
+        *n_lo = *n_hi = 0;
+        if (np == 0) return CPIC_OK;
+        cudaMemsetAsync(mig_counters, 0, 8 * sizeof(unsigned), stream);
+        const int plane = g.gx * g.gy;
+        k_extract_mark<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, plane, g.nz, carve_sendbuf<R>(lo, cap_send),
+                                                             carve_sendbuf<R>(hi, cap_send), cap_send, rebase_lo, rebase_hi, mig_counters);
+        if ((rc = check_launch("k_extract_mark"))) return rc;
+        unsigned h[3];
+        if ((rc = cuda(cudaMemcpyAsync(h, mig_counters, sizeof h, cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(stream), "extract_z_leavers"))) return rc;
+        if (h[2] || h[0] > cap_send || h[1] > cap_send)
+            return fail(CPIC_E_CAPACITY, "extract_z_leavers: %u/%u leavers exceed the send-buffer capacity %lld", h[0], h[1], cap_send);
+        *n_lo = h[0]; *n_hi = h[1];
+        const long long n_out = (long long)h[0] + h[1];
+        if (n_out == 0) return CPIC_OK;
+        const long long np_new = np - n_out;
+        k_extract_lists<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, np_new, plane, g.nz, mig_lists, mig_cap, mig_counters);
+        if ((rc = check_launch("k_extract_lists"))) return rc;
+        k_extract_fill<R><<<blocks_for(n_out), 256, 0, stream>>>(P[cur], mig_lists, mig_cap, mig_counters);
+        if ((rc = check_launch("k_extract_fill"))) return rc;
+        np = np_new;
+        return CPIC_OK;
+    }
+    int append_device(const void* buf, long long cap_buf, long long n) override {
+        if (n < 0 || n > cap_buf) return fail(CPIC_E_INVALID, "append_particles_device: bad count");
+        if (np + n > cap) return fail(CPIC_E_CAPACITY, "append_particles_device: %lld + %lld particles exceed capacity %lld", np, n, cap);
+        if (n == 0) return CPIC_OK;
+        SendBuf<R> b = carve_sendbuf<R>(const_cast<void*>(buf), cap_buf);
+        Particles<R>& p = P[cur];
+        R* dst[7] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w};
+        int rc;
+        for (int k = 0; k < 7; ++k)
+            if ((rc = cuda(cudaMemcpyAsync(dst[k] + np, b.m[k], (size_t)n * sizeof(R), cudaMemcpyDeviceToDevice, stream), "D2D append"))) return rc;
+        if ((rc = cuda(cudaMemcpyAsync(p.cell + np, b.cell, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, stream), "D2D append"))) return rc;
+        np += n;
+        return CPIC_OK;
+    }
     int update_ghosts(int which) override {
         if (which == 0) return ghost_fold();
+        if (which == 3) return fold_phase(0);
+        if (which == 4) return fold_phase(1);
         if (which == 1) return ghost_copy(F_JFX);
         if (which == 2) return ghost_copy(F_CBX);
         return fail(CPIC_E_INVALID, "update_ghosts: which=%d", which);
+    }
+    int stencil_only(int which, double px, double py, double pz, double dt_eps0) override {
+        if (which == 0) {
+            if (prm.solver == CPIC_SOLVER_ES_1D) return CPIC_OK;
+            Box b{1, 1, 1, g.nx, g.ny, g.nz};
+            k_advance_b<R><<<blocks_for(b.count()), 256, 0, stream>>>(F(), g, b, (R)px, (R)py, (R)pz);
+            return check_launch("k_advance_b");
+        }
+        if (prm.solver == CPIC_SOLVER_ES_1D) {
+            k_advance_e_es<R><<<blocks_for(g.nc), 256, 0, stream>>>(F(), g.nc, (R)dt_eps0);
+            return check_launch("k_advance_e_es");
+        }
+        Box b{1, 1, 1, g.nx + 1, g.ny + 1, g.nz + 1};
+        k_advance_e_em<R><<<blocks_for(b.count()), 256, 0, stream>>>(F(), g, b, (R)px, (R)py, (R)pz, (R)dt_eps0);
+        return check_launch("k_advance_e_em");
     }
     int advance_b(double px, double py, double pz) override {
         if (prm.solver == CPIC_SOLVER_ES_1D) return CPIC_OK;  // src/fields.h:470-482: no-op
@@ -343,7 +423,7 @@ struct Ctx final : CtxBase {
         a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
         a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
         a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.ng = g.ng; a.gx = g.gx; a.gy = g.gy;
-        a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC;
+        a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC ? g.per : 0;
         a.stats = stats;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
@@ -641,6 +721,31 @@ int cpic_set_num_particles(cpic_ctx* ctx, int64_t n) {
     if (n < 0 || n > c->prm.max_particles) return c->fail(CPIC_E_CAPACITY, "set_num_particles: %lld out of range", (long long)n);
     c->np = n;
     return CPIC_OK;
+}
+
+int cpic_advance_b_stencil(cpic_ctx* ctx, double px, double py, double pz) { CTX_OR_FAIL(ctx); return c->stencil_only(0, px, py, pz, 0.0); }
+int cpic_advance_e_stencil(cpic_ctx* ctx, double px, double py, double pz, double dt_eps0) { CTX_OR_FAIL(ctx); return c->stencil_only(1, px, py, pz, dt_eps0); }
+
+int cpic_set_axis_periodic(cpic_ctx* ctx, int32_t px, int32_t py, int32_t pz) {
+    CTX_OR_FAIL(ctx);
+    c->g.per = (px ? 1 : 0) | (py ? 2 : 0) | (pz ? 4 : 0);
+    return CPIC_OK;
+}
+
+int cpic_extract_z_leavers(cpic_ctx* ctx, void* lo_buf, void* hi_buf, int64_t capacity, int64_t* n_lo, int64_t* n_hi,
+                           int32_t rebase_lo, int32_t rebase_hi) {
+    CTX_OR_FAIL(ctx);
+    if (!lo_buf || !hi_buf || !n_lo || !n_hi) return c->fail(CPIC_E_INVALID, "extract_z_leavers: null argument");
+    long long a = 0, b = 0;
+    int rc = c->extract_z(lo_buf, hi_buf, capacity, &a, &b, rebase_lo, rebase_hi);
+    *n_lo = a; *n_hi = b;
+    return rc;
+}
+
+int cpic_append_particles_device(cpic_ctx* ctx, const void* buf, int64_t capacity, int64_t n) {
+    CTX_OR_FAIL(ctx);
+    if (!buf && n > 0) return c->fail(CPIC_E_INVALID, "append_particles_device: null buffer");
+    return c->append_device(buf, capacity, n);
 }
 
 int cpic_set_modes(cpic_ctx* ctx, int32_t fp_mode, int32_t deposit_mode) {

@@ -13,6 +13,8 @@ struct Grid {
     int gx, gy, gz;      // n + 2*ng
     int sy, sz;          // strides: sy = gx, sz = gx*gy
     long long nc;        // gx*gy*gz
+    int per;             // bit a set: axis a (0 x, 1 y, 2 z) is periodic inside this context; a cleared bit
+                         // means the ghost layer along that axis belongs to a neighbouring slab (multi-GPU)
 };
 
 inline Grid make_grid(int nx, int ny, int nz, int ng) {
@@ -21,6 +23,7 @@ inline Grid make_grid(int nx, int ny, int nz, int ng) {
     g.gx = nx + 2 * ng; g.gy = ny + 2 * ng; g.gz = nz + 2 * ng;
     g.sy = g.gx; g.sz = g.gx * g.gy;
     g.nc = (long long)g.gx * g.gy * g.gz;
+    g.per = 7;
     return g;
 }
 

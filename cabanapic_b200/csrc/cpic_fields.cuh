@@ -101,7 +101,11 @@ __global__ void __launch_bounds__(256) k_ghost_copy3(R* __restrict__ a, R* __res
     const int y = (int)(row - (long long)z * g.gy);
     const int wx = (x == 0) ? g.nx : (x == g.nx + 1 ? 1 : x);
     const int wy = (y == 0) ? g.ny : (y == g.ny + 1 ? 1 : y);
-    const int wz = (z == 0) ? g.nz : (z == g.nz + 1 ? 1 : z);
+    int wz = (z == 0) ? g.nz : (z == g.nz + 1 ? 1 : z);
+    if (!(g.per & 4)) {           // z ghosts belong to the neighbouring slab: filled by the plane exchange
+        if (wz != z) return;
+        wz = z;
+    }
     if (wx == x && wy == y && wz == z) return;
     const long long s = wx + (long long)g.sy * wy + (long long)g.sz * wz;
     a[t] = a[s]; b3[t] = b3[s]; c[t] = c[s];
@@ -116,6 +120,8 @@ __global__ void __launch_bounds__(256) k_ghost_fold(R* __restrict__ jx, R* __res
     const int comp = blockIdx.y;
     const long long t = blockIdx.x * 256LL + threadIdx.x;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
+    // slab mode (z not periodic here): the z folds are done by the host from the neighbour's plane
+    if (!(g.per & 4) && ((comp == 0 && PHASE == 1) || (comp == 1 && PHASE == 0))) return;
     const long long sy = g.sy, sz = g.sz;
     long long to, from;
     R* v;

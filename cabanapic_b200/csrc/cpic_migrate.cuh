@@ -1,0 +1,82 @@
+// Particle migration between z-slabs (multi-GPU slab mode; new work -- the reference is single
+// process, its only traces of this are the commented neighbour logic in src/move_p.h:327-346).
+//
+// With the z axis not periodic inside a context, the mover leaves a particle that crossed the
+// slab's low/high z face in the ghost plane z = 0 / z = nz+1 (what the reference does for any
+// non-periodic boundary, src/move_p.h:257-352).  These kernels pull such particles out of the
+// store into two struct-of-arrays send buffers (cell index already re-based to the receiving
+// slab's numbering) and close the holes they leave, so the store stays dense.
+//
+// Send buffer layout (both buffers, capacity `cap` particles): member m (dx dy dz ux uy uz w) at
+// byte offset m*cap*sizeof(R); cell (int32) at byte offset 7*cap*sizeof(R).
+#pragma once
+#include "cpic_common.cuh"
+#include "cpic_particles.cuh"
+
+namespace cpic {
+
+template <class R>
+struct SendBuf {
+    R* m[7];
+    int* cell;
+};
+template <class R>
+inline SendBuf<R> carve_sendbuf(void* base, long long cap) {
+    SendBuf<R> b;
+    char* p = static_cast<char*>(base);
+    for (int k = 0; k < 7; ++k) b.m[k] = reinterpret_cast<R*>(p + (size_t)k * cap * sizeof(R));
+    b.cell = reinterpret_cast<int*>(p + (size_t)7 * cap * sizeof(R));
+    return b;
+}
+
+__device__ __forceinline__ int z_side(int cell, int plane, int nz) {   // 0: stays, 1: low ghost, 2: high ghost
+    const int iz = cell / plane;
+    return iz == 0 ? 1 : (iz == nz + 1 ? 2 : 0);
+}
+
+// counters: [0] n_lo, [1] n_hi, [2] overflow flag
+template <class R>
+__global__ void __launch_bounds__(256) k_extract_mark(Particles<R> p, long long np, int plane, int nz, SendBuf<R> lo,
+                                                      SendBuf<R> hi, long long cap, int rebase_lo, int rebase_hi,
+                                                      unsigned* __restrict__ counters) {
+    const long long n = blockIdx.x * 256LL + threadIdx.x;
+    if (n >= np) return;
+    const int c = p.cell[n];
+    const int side = z_side(c, plane, nz);
+    if (!side) return;
+    const unsigned slot = atomicAdd(counters + (side - 1), 1u);
+    if (slot >= cap) { counters[2] = 1u; return; }
+    SendBuf<R>& b = side == 1 ? lo : hi;
+    b.m[0][slot] = p.dx[n]; b.m[1][slot] = p.dy[n]; b.m[2][slot] = p.dz[n];
+    b.m[3][slot] = p.ux[n]; b.m[4][slot] = p.uy[n]; b.m[5][slot] = p.uz[n]; b.m[6][slot] = p.w[n];
+    b.cell[slot] = c + (side == 1 ? rebase_lo : rebase_hi);
+}
+
+// After the counts are known: np_new = np - n_out.  Holes at index < np_new are filled with the
+// staying particles found at index >= np_new (there are exactly as many).  lists: [0..cap) hole
+// indices, [cap..2cap) donor indices; counters [3] n_holes, [4] n_donors.
+template <class R>
+__global__ void __launch_bounds__(256) k_extract_lists(Particles<R> p, long long np, long long np_new, int plane, int nz,
+                                                       unsigned* __restrict__ lists, long long cap,
+                                                       unsigned* __restrict__ counters) {
+    const long long n = blockIdx.x * 256LL + threadIdx.x;
+    if (n >= np) return;
+    const bool leaving = z_side(p.cell[n], plane, nz) != 0;
+    if (n < np_new) {
+        if (leaving) lists[atomicAdd(counters + 3, 1u)] = (unsigned)n;
+    } else if (!leaving) {
+        lists[cap + atomicAdd(counters + 4, 1u)] = (unsigned)n;
+    }
+}
+template <class R>
+__global__ void __launch_bounds__(256) k_extract_fill(Particles<R> p, const unsigned* __restrict__ lists, long long cap,
+                                                      const unsigned* __restrict__ counters) {
+    const long long j = blockIdx.x * 256LL + threadIdx.x;
+    if (j >= counters[3]) return;
+    const unsigned h = lists[j], d = lists[cap + j];
+    p.dx[h] = p.dx[d]; p.dy[h] = p.dy[d]; p.dz[h] = p.dz[d];
+    p.ux[h] = p.ux[d]; p.uy[h] = p.uy[d]; p.uz[h] = p.uz[d];
+    p.w[h] = p.w[d]; p.cell[h] = p.cell[d];
+}
+
+}  // namespace cpic

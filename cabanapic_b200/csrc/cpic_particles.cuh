@@ -34,7 +34,7 @@ struct PushArgs {
     R* acc;        // [nc][12]
     R qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
     int nx, ny, nz, ng, gx, gy;
-    int periodic;
+    int periodic;     // bit a: wrap along axis a (0 x, 1 y, 2 z); cleared: the particle stays in the ghost cell
     int dep_thresh;   // mixed warps: runs at least this long are warp-reduced, shorter ones use direct atomics
     int dep_rounds;   // mixed warps: at most this many peel rounds before falling back to direct atomics
     unsigned long long* stats;  // optional: [0] movers [1] crossings [2..7] wraps per face
@@ -232,14 +232,18 @@ __device__ __forceinline__ int cross_face(int& ii, int axis, R dirv, const PushA
     if (face == 3) ix++;
     if (face == 4) iy++;
     if (face == 5) iz++;
+    // detect_leaving_domain: later tests override earlier ones.  a.periodic is a per-axis mask
+    // (7 = the reference); an axis whose bit is clear (slab mode: that ghost layer belongs to a
+    // neighbour) neither wraps nor hides the wrap of another axis, so its tests are skipped.
+    const int per = a.periodic;
     int leaving = -1;
-    if (ix == 0) leaving = 0;
-    if (iy == 0) leaving = 1;
-    if (iz == 0) leaving = 2;
-    if (ix == a.nx + 1) leaving = 3;
-    if (iy == a.ny + 1) leaving = 4;
-    if (iz == a.nz + 1) leaving = 5;
-    if (leaving >= 0 && a.periodic) {
+    if ((per & 1) && ix == 0) leaving = 0;
+    if ((per & 2) && iy == 0) leaving = 1;
+    if ((per & 4) && iz == 0) leaving = 2;
+    if ((per & 1) && ix == a.nx + 1) leaving = 3;
+    if ((per & 2) && iy == a.ny + 1) leaving = 4;
+    if ((per & 4) && iz == a.nz + 1) leaving = 5;
+    if (leaving >= 0) {
         if (leaving == 0) ix = (a.nx - 1) + a.ng;
         else if (leaving == 1) iy = (a.ny - 1) + a.ng;
         else if (leaving == 2) iz = (a.nz - 1) + a.ng;

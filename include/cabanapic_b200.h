@@ -131,7 +131,7 @@ int  cpic_advance_b(cpic_ctx* ctx, double px, double py, double pz);     /* src/
 int  cpic_advance_e(cpic_ctx* ctx, double px, double py, double pz, double dt_eps0); /* src/fields.h:365-378, 618-665, 511-544 */
 int  cpic_uncenter_particles(cpic_ctx* ctx, double qdt_2mc);      /* src/uncenter_p.h:4-105       */
 int  cpic_energies(cpic_ctx* ctx, double* e_energy, double* b_energy);   /* src/fields.h:556-615, 484-509 */
-int  cpic_update_ghosts(cpic_ctx* ctx, int which /* 0: fold J, 1: copy J, 2: copy cB */); /* src/fields.h:11-271 */
+int  cpic_update_ghosts(cpic_ctx* ctx, int which /* 0: fold J, 1: copy J, 2: copy cB, 3 / 4: first / second sweep of the J fold only */); /* src/fields.h:11-271 */
 
 /* n whole steps in the reference's order (example/example.cpp:221-266), fused on the
  * device: no host synchronisation between steps.  sort_interval > 0 re-sorts the particles
@@ -160,6 +160,26 @@ int  cpic_device_ptr(cpic_ctx* ctx, int which, void** ptr, int64_t* count, int64
 int  cpic_set_stream(cpic_ctx* ctx, void* cuda_stream);
 int  cpic_set_num_particles(cpic_ctx* ctx, int64_t n);   /* after an external particle exchange */
 int  cpic_set_modes(cpic_ctx* ctx, int32_t fp_mode, int32_t deposit_mode);
+
+/* Multi-GPU z-slab decomposition (new: the reference is single-process).
+ * cpic_set_axis_periodic clears the periodic wrap along chosen axes inside this context: the mover
+ * then leaves a particle that crossed such a face in the ghost cell (the reference's behaviour for a
+ * non-periodic boundary, src/move_p.h:257-352) and the ghost fold/copy kernels skip that axis (the
+ * host exchanges those planes with the neighbouring slab).
+ * cpic_extract_z_leavers removes the particles sitting in the ghost planes z = 0 (-> lo_buf) and
+ * z = nz+1 (-> hi_buf) from the store, keeps the store dense, and adds rebase_lo / rebase_hi to their
+ * cell index (the receiving slab's numbering).  Buffers are DEVICE memory, capacity particles each,
+ * struct-of-arrays: member m at byte m*capacity*real_bytes, cell (int32) at byte 7*capacity*real_bytes.
+ * cpic_append_particles_device appends n particles from such a buffer.  Both block the host. */
+int  cpic_set_axis_periodic(cpic_ctx* ctx, int32_t px, int32_t py, int32_t pz);
+/* The stencil kernels of advance_b / advance_e alone (src/fields.h:692-717 / 646-664, 534-543), without the
+ * ghost fold / copy calls that the reference makes inside them (:718, :642-643): in slab mode the host
+ * interleaves those with the neighbour exchange. */
+int  cpic_advance_b_stencil(cpic_ctx* ctx, double px, double py, double pz);
+int  cpic_advance_e_stencil(cpic_ctx* ctx, double px, double py, double pz, double dt_eps0);
+int  cpic_extract_z_leavers(cpic_ctx* ctx, void* lo_buf, void* hi_buf, int64_t capacity, int64_t* n_lo, int64_t* n_hi,
+                            int32_t rebase_lo, int32_t rebase_hi);
+int  cpic_append_particles_device(cpic_ctx* ctx, const void* buf, int64_t capacity, int64_t n);
 
 /* Device-side timing of the last call of each kind, in milliseconds (CUDA events on the
  * context's stream).  what: 0 push, 1 sort, 2 field side (interp+unload+advance), 3 step total. */

@@ -108,7 +108,8 @@ class Restatement:
     def push(self, s, k: Consts, periodic=True):
         ncross = C.c_long(0)
         movers = self.lib.orc_push(*[_ptr(s.p[n]) for n in PARTICLE_NAMES], C.c_long(s.np), _ptr(s.interp),
-                                   _ptr(s.acc), C.byref(k), *self._grid(s), C.c_int(1 if periodic else 0),
+                                   _ptr(s.acc), C.byref(k), *self._grid(s),
+                                   C.c_int(7 if periodic is True else int(periodic)),
                                    C.byref(ncross))
         return int(movers), int(ncross.value)
 
@@ -135,6 +136,21 @@ class Restatement:
 
     def ghost_fold(self, s, comps):
         self.lib.orc_ghost_fold(*[_ptr(s.f[c]) for c in comps], *self._grid(s))
+
+    # slab-mode helpers (multi-GPU tests; see the comment in cpic_oracle.c)
+    def ghost_copy_axes(self, s, comps, per):
+        self.lib.orc_ghost_copy_axes(*[_ptr(s.f[c]) for c in comps], *self._grid(s), C.c_int(per))
+
+    def ghost_fold_phase(self, s, phase, per):
+        self.lib.orc_ghost_fold_phase(*[_ptr(s.f[c]) for c in (6, 7, 8)], *self._grid(s), C.c_int(phase), C.c_int(per))
+
+    def advance_b_stencil(self, s, px, py, pz):
+        self.lib.orc_advance_b_stencil(_ptr_array(list(s.f)), C.c_double(px), C.c_double(py), C.c_double(pz),
+                                       *self._grid(s))
+
+    def advance_e_stencil(self, s, px, py, pz, dt_eps0):
+        self.lib.orc_advance_e_stencil(_ptr_array(list(s.f)), C.c_double(px), C.c_double(py), C.c_double(pz),
+                                       *self._grid(s), C.c_double(dt_eps0))
 
     def energies(self, s, solver=0):
         e, b = C.c_double(), C.c_double()

@@ -181,8 +181,20 @@ static int move_particle(real* px, real* py, real* pz, int* pcell, real* acc, re
                 if (face == 4) iy++;
                 if (face == 5) iz++;
                 {
-                    const int lv = leaving_domain(nx, ny, nz, ix, iy, iz);
-                    if (lv >= 0 && periodic) {          /* :257-288 */
+                    /* periodic = per-axis bit mask (7 = the reference).  An axis whose bit is clear
+                     * (slab mode: that ghost layer belongs to a neighbour) neither wraps nor hides
+                     * the wrap of another axis, so its tests are skipped. */
+                    int lv = leaving_domain(nx, ny, nz, ix, iy, iz);
+                    if (periodic != 7) {
+                        lv = -1;
+                        if ((periodic & 1) && ix == 0) lv = 0;
+                        if ((periodic & 2) && iy == 0) lv = 1;
+                        if ((periodic & 4) && iz == 0) lv = 2;
+                        if ((periodic & 1) && ix == nx + 1) lv = 3;
+                        if ((periodic & 2) && iy == ny + 1) lv = 4;
+                        if ((periodic & 4) && iz == nz + 1) lv = 5;
+                    }
+                    if (lv >= 0) {                      /* :257-288 */
                         if (lv == 0) ix = (nx - 1) + ng;
                         else if (lv == 1) iy = (ny - 1) + ng;
                         else if (lv == 2) iz = (nz - 1) + ng;
@@ -408,6 +420,86 @@ void orc_advance_e_es1d(real* const* f, long nx, long ny, long nz, long ng, doub
     }
 }
 
+/* ---- slab-mode helpers (multi-GPU tests only; NOT in the reference, which is single-domain).
+ * They are the pieces of the functions above with the z-direction ghost work left out, so a
+ * test can interleave a z-plane exchange between ranks exactly where the periodic z copy/fold
+ * would have happened.  per = axis bit mask (1 x, 2 y, 4 z) of the axes handled locally. */
+void orc_ghost_copy_axes(real* a, real* b, real* c, long nx, long ny, long nz, long ng, int per) {
+    real* s[3] = {a, b, c};
+    for (int m = 0; m < 3; ++m) {
+        real* v = s[m];
+        if (per & 1)
+            for (long z = 1; z < nz + 1; ++z)
+                for (long y = 1; y < ny + 1; ++y) {
+                    v[vox(nx + 1, y, z, nx, ny, ng)] = v[vox(1, y, z, nx, ny, ng)];
+                    v[vox(0, y, z, nx, ny, ng)] = v[vox(nx, y, z, nx, ny, ng)];
+                }
+        if (per & 2)
+            for (long x = 0; x < nx + 2; ++x)
+                for (long z = 1; z < nz + 1; ++z) {
+                    v[vox(x, ny + 1, z, nx, ny, ng)] = v[vox(x, 1, z, nx, ny, ng)];
+                    v[vox(x, 0, z, nx, ny, ng)] = v[vox(x, ny, z, nx, ny, ng)];
+                }
+        if (per & 4)
+            for (long y = 0; y < ny + 2; ++y)
+                for (long x = 0; x < nx + 2; ++x) {
+                    v[vox(x, y, nz + 1, nx, ny, ng)] = v[vox(x, y, 1, nx, ny, ng)];
+                    v[vox(x, y, 0, nx, ny, ng)] = v[vox(x, y, nz, nx, ny, ng)];
+                }
+    }
+}
+/* first (phase 0) or second (phase 1) sweep of every component's fold; z folds only if per & 4 */
+void orc_ghost_fold_phase(real* jx, real* jy, real* jz, long nx, long ny, long nz, long ng, int phase, int per) {
+    if (phase == 0) {
+        for (long x = 1; x <= nx; ++x)
+            for (long z = 1; z <= nz + 1; ++z) jx[vox(x, 1, z, nx, ny, ng)] += jx[vox(x, ny + 1, z, nx, ny, ng)];
+        if (per & 4)
+            for (long y = 1; y <= ny; ++y)
+                for (long x = 1; x <= nx + 1; ++x) jy[vox(x, y, 1, nx, ny, ng)] += jy[vox(x, y, nz + 1, nx, ny, ng)];
+        for (long z = 1; z <= nz; ++z)
+            for (long y = 1; y <= ny + 1; ++y) jz[vox(1, y, z, nx, ny, ng)] += jz[vox(nx + 1, y, z, nx, ny, ng)];
+    } else {
+        if (per & 4)
+            for (long x = 1; x <= nx; ++x)
+                for (long y = 1; y <= ny + 1; ++y) jx[vox(x, y, 1, nx, ny, ng)] += jx[vox(x, y, nz + 1, nx, ny, ng)];
+        for (long y = 1; y <= ny; ++y)
+            for (long z = 1; z <= nz + 1; ++z) jy[vox(1, y, z, nx, ny, ng)] += jy[vox(nx + 1, y, z, nx, ny, ng)];
+        for (long z = 1; z <= nz; ++z)
+            for (long x = 1; x <= nx + 1; ++x) jz[vox(x, 1, z, nx, ny, ng)] += jz[vox(x, ny + 1, z, nx, ny, ng)];
+    }
+}
+void orc_advance_b_stencil(real* const* f, double px_, double py_, double pz_, long nx, long ny, long nz, long ng) {
+    const real px = (real)px_, py = (real)py_, pz = (real)pz_;
+    const real *ex = f[F_EX], *ey = f[F_EY], *ez = f[F_EZ];
+    real *cbx = f[F_CBX], *cby = f[F_CBY], *cbz = f[F_CBZ];
+    for (long x = 1; x < nx + 1; ++x)
+        for (long y = 1; y < ny + 1; ++y)
+            for (long z = 1; z < nz + 1; ++z) {
+                const long f0 = vox(x, y, z, nx, ny, ng), fx = vox(x + 1, y, z, nx, ny, ng),
+                           fy = vox(x, y + 1, z, nx, ny, ng), fz = vox(x, y, z + 1, nx, ny, ng);
+                cbx[f0] -= (py * (ez[fy] - ez[f0]) - pz * (ey[fz] - ey[f0]));
+                cby[f0] -= (pz * (ex[fz] - ex[f0]) - px * (ez[fx] - ez[f0]));
+                cbz[f0] -= (px * (ey[fx] - ey[f0]) - py * (ex[fy] - ex[f0]));
+            }
+}
+void orc_advance_e_stencil(real* const* f, double px_, double py_, double pz_, long nx, long ny, long nz, long ng,
+                           double dt_eps0) {
+    const real px = (real)px_, py = (real)py_, pz = (real)pz_;
+    const real cj = (real)dt_eps0;
+    real *ex = f[F_EX], *ey = f[F_EY], *ez = f[F_EZ];
+    const real *cbx = f[F_CBX], *cby = f[F_CBY], *cbz = f[F_CBZ];
+    const real *jfx = f[F_JFX], *jfy = f[F_JFY], *jfz = f[F_JFZ];
+    for (long x = 1; x < nx + 2; ++x)
+        for (long y = 1; y < ny + 2; ++y)
+            for (long z = 1; z < nz + 2; ++z) {
+                const long f0 = vox(x, y, z, nx, ny, ng), fx = vox(x - 1, y, z, nx, ny, ng),
+                           fy = vox(x, y - 1, z, nx, ny, ng), fz = vox(x, y, z - 1, nx, ny, ng);
+                ex[f0] = ex[f0] + (-cj * jfx[f0]) + (py * (cbz[f0] - cbz[fy]) - pz * (cby[f0] - cby[fz]));
+                ey[f0] = ey[f0] + (-cj * jfy[f0]) + (pz * (cbx[f0] - cbx[fz]) - px * (cbz[f0] - cbz[fx]));
+                ez[f0] = ez[f0] + (-cj * jfz[f0]) + (px * (cby[f0] - cby[fx]) - py * (cbx[f0] - cbx[fy]));
+            }
+}
+
 /* src/fields.h:556-615 (EM: interior) and :484-509 (ES_1D: every cell);
  * accumulated in real like the reference's parallel_reduce, x outermost. */
 void orc_energies(real* const* f, int solver, long nx, long ny, long nz, long ng, double* e, double* b) {
@@ -444,7 +536,7 @@ void orc_step(real* dx, real* dy, real* dz, real* ux, real* uy, real* uz, const 
     for (long s = 0; s < nsteps; ++s) {
         orc_load_interpolator(f, ip, nx, ny, nz, ng);
         orc_clear_accumulator(acc, nc);
-        orc_push(dx, dy, dz, ux, uy, uz, w, cell, np, ip, acc, k, nx, ny, nz, ng, 1, 0);
+        orc_push(dx, dy, dz, ux, uy, uz, w, cell, np, ip, acc, k, nx, ny, nz, ng, 7, 0);
         orc_unload_accumulator(f, acc, nx, ny, nz, ng, k);
         if (solver == 0) {
             orc_advance_b(f, hpx, hpy, hpz, nx, ny, nz, ng);

@@ -386,3 +386,110 @@ def test_energy_history_2stream_em_float_vs_gold():
     window = (lines >= 3581) & (lines < 4881)
     assert erel[lines < 3581].max() < 5e-3, erel[lines < 3581].max()
     assert rel[window].max() < 0.25, rel[window].max()
+
+
+# ----------------------------------------------------------------------------- slab-mode pieces
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_slab_mode_kernels_vs_oracle(prec):
+    """The single-GPU pieces of the z-slab mode (cabanapic_b200/dist.py): push with the z wrap
+    switched off (particles stay in the ghost planes; x/y wraps still apply there), the x/y-only
+    ghost fold sweeps and ghost copy, the bare stencils, and the extraction of the ghost-plane
+    particles with cell re-basing.  Bars: particles and fields bit-exact, accumulators to
+    summation order, the extracted sets equal as multisets."""
+    import torch
+    nx, ny, nz = 6, 5, 4
+    s = random_state(nx, ny, nz, nppc=16, prec=prec, seed=9)
+    rng = np.random.default_rng(2)
+    s.f[6:] = rng.standard_normal(s.f[6:].shape).astype(PREC[prec])
+    k = consts_for(nx, ny, nz, prec)
+    O = Restatement(prec)
+    plane = (nx + 2) * (ny + 2)
+    with make_ctx(s) as c:
+        c.set_axis_periodic(1, 1, 0)
+        # field-side pieces on junk J
+        for ph in (0, 1):
+            O.ghost_fold_phase(s, ph, 3); c.update_ghosts(3 + ph)
+            assert np.array_equal(c.download_fields(), s.f)
+        O.ghost_copy_axes(s, (6, 7, 8), 3); c.update_ghosts(1)
+        assert np.array_equal(c.download_fields(), s.f)
+        hp = (0.5 * k.px, 0.5 * k.py, 0.5 * k.pz)
+        O.advance_b_stencil(s, *hp); c.advance_b_stencil(*hp)
+        O.ghost_copy_axes(s, (3, 4, 5), 3); c.update_ghosts(2)
+        O.advance_e_stencil(s, k.px, k.py, k.pz, k.dt_eps0); c.advance_e_stencil(k.px, k.py, k.pz, k.dt_eps0)
+        assert np.array_equal(c.download_fields(), s.f)
+        # push without the z wrap
+        O.load_interpolator(s); c.load_interpolator_array()
+        O.clear_accumulator(s); c.clear_accumulator_array()
+        O.push(s, k, periodic=3); c.push(to_k(k))
+        p = c.download_particles()
+        for n in PARTICLE_NAMES:
+            assert np.array_equal(p[n], s.p[n]), n
+        assert acc_close(c.download_accumulators(), s.acc, prec)
+        iz = s.p["cell"] // plane
+        n_lo, n_hi = int((iz == 0).sum()), int((iz == nz + 1).sum())
+        assert n_lo > 5 and n_hi > 5
+        # extraction
+        rb = np.dtype(PREC[prec]).itemsize
+        cap = max(n_lo, n_hi) + 7
+        lo = torch.zeros(cap * (7 * rb + 4), dtype=torch.uint8, device="cuda")
+        hi = torch.zeros_like(lo)
+        with pytest.raises(cp().CpicError) as err:          # send buffers too small: loud, store untouched
+            c.extract_z_leavers(lo.data_ptr(), hi.data_ptr(), 2, 0, 0)
+        assert err.value.code == -4 and c.num_particles == s.np
+        got = c.extract_z_leavers(lo.data_ptr(), hi.data_ptr(), cap, 3 * plane, -nz * plane)
+        assert got == (n_lo, n_hi)
+        assert c.num_particles == s.np - n_lo - n_hi
+        rest = c.download_particles()
+
+        def unpack(buf, n):
+            b = buf.cpu().numpy()
+            d = {m: b[j * cap * rb: j * cap * rb + n * rb].view(PREC[prec]).copy() for j, m in enumerate(PARTICLE_NAMES[:7])}
+            d["cell"] = b[7 * cap * rb: 7 * cap * rb + n * 4].view(np.int32).copy()
+            return d
+        for buf, n, sel, rebase in ((lo, n_lo, iz == 0, 3 * plane), (hi, n_hi, iz == nz + 1, -nz * plane)):
+            d = unpack(buf, n)
+            want = {m: s.p[m][sel] for m in PARTICLE_NAMES}
+            want["cell"] = want["cell"] + rebase
+            a, b = canonical_order(d), canonical_order(want)
+            for m in PARTICLE_NAMES:
+                assert np.array_equal(d[m][a], want[m][b]), m
+        keep = (iz != 0) & (iz != nz + 1)
+        want = {m: s.p[m][keep] for m in PARTICLE_NAMES}
+        a, b = canonical_order(rest), canonical_order(want)
+        for m in PARTICLE_NAMES:
+            assert np.array_equal(rest[m][a], want[m][b]), m
+        # append brings them back
+        c.append_particles_device(lo.data_ptr(), cap, n_lo)
+        c.append_particles_device(hi.data_ptr(), cap, n_hi)
+        assert c.num_particles == s.np
+
+
+def test_slab_stepper_single_rank_equals_fused_step():
+    """world_size 1 run of the slab stepper (exchanges degenerate to local copies) against
+    cpic_step on the same state: the choreography through GpuEngine reproduces the fused step.
+    Fields to 2e-5 of scale (the ghost-plane accumulator rows are added as a lump), cells exact."""
+    import torch
+    from cabanapic_b200.dist import GpuEngine, SlabStepper
+    m = cp()
+    nx, ny, nz, prec = 6, 5, 7, "f32"
+    s = random_state(nx, ny, nz, nppc=20, prec=prec, seed=3)
+    k = to_k(consts_for(nx, ny, nz, prec))
+    with make_ctx(s) as c:
+        c.step(k, 5, 0, False)
+        p_ref, f_ref = c.download_particles(), c.download_fields()
+    e = GpuEngine(nx, ny, nz, s.np + 100, real=np.float32, z_periodic=False)
+    try:
+        e.ctx.upload_particles(s.p)
+        e.ctx.upload_fields(s.f)
+        st = SlabStepper(e, k, 0, 1, nz, nz, send_capacity=s.np)
+        for _ in range(5):
+            st.step()
+        p, f = e.ctx.download_particles(), e.ctx.download_fields()
+        assert st.migrated[0] > 0 and st.migrated[1] > 0
+    finally:
+        e.close()
+    a, b = canonical_order(p), canonical_order(p_ref)
+    assert np.mean(p["cell"][a] == p_ref["cell"][b]) > 0.999
+    scale = np.abs(f_ref).max(axis=1, keepdims=True) + 1e-30
+    interior = np.zeros((nz + 2, ny + 2, nx + 2), bool); interior[1:-1, 1:-1, 1:-1] = True
+    assert (np.abs(f - f_ref) / scale)[:6, interior.ravel()].max() < 1e-4
