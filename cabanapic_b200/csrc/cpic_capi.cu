@@ -17,6 +17,7 @@
 #include "cpic_common.cuh"
 #include "cpic_fields.cuh"
 #include "cpic_particles.cuh"
+#include "cpic_push2.cuh"
 #include "cpic_sort.cuh"
 #include "cpic_init.cuh"
 #include "cpic_migrate.cuh"
@@ -146,6 +147,8 @@ struct Ctx final : CtxBase {
         // developer tuning knobs (not part of the ABI)
         if (const char* e = getenv("CPIC_PUSH_PREFETCH")) push_prefetch = atoi(e) != 0;
         if (const char* e = getenv("CPIC_PUSH_GRID")) push_grid = atoi(e);
+        if (const char* e = getenv("CPIC_PUSH_V1")) use_push2 = atoi(e) == 0;
+        if (const char* e = getenv("CPIC_PUSH2_FASTDS")) push2_fastds = atoi(e) != 0;
         if (const char* e = getenv("CPIC_DEP_THRESH")) dep_thresh = atoi(e);
         if (const char* e = getenv("CPIC_DEP_ROUNDS")) dep_rounds = atoi(e);
         nc_pad = (g.nc + 63) / 64 * 64;
@@ -417,12 +420,31 @@ struct Ctx final : CtxBase {
         if (want_stats) return push_prefetch ? launch_push_k<FMA, DEP, true, true>(a) : launch_push_k<FMA, DEP, true, false>(a);
         return push_prefetch ? launch_push_k<FMA, DEP, false, true>(a) : launch_push_k<FMA, DEP, false, false>(a);
     }
+    // second-generation float kernel (packed FP32x2, two particles per thread); deposit mode WARP only
+    bool use_push2 = true, push2_fastds = true;
+    template <bool FMA, bool ST, bool FD>
+    int launch_push2(const PushArgs<float>& a) {
+        auto kern = k_push2<FMA, ST, FD>;
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PUSH2_WARPS * 32, 0);
+        if (per_sm < 1) per_sm = 1;
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device);
+        long long blocks = (long long)sms * per_sm;
+        const long long need = (np + PUSH2_WARPS * 64 - 1) / (PUSH2_WARPS * 64);
+        if (blocks > need) blocks = need;
+        if (push_grid > 0) blocks = std::min<long long>(push_grid, need);
+        volatile float one = 1.0f;     // a runtime value as far as the compiler is concerned (cpic_push2.cuh)
+        kern<<<(unsigned)blocks, PUSH2_WARPS * 32, 0, stream>>>(a, one);
+        return check_launch("k_push2");
+    }
     int push(const cpic_consts& k) override {
         if (np == 0) return CPIC_OK;
         PushArgs<R> a;
         a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
         a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
         a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.ng = g.ng; a.gx = g.gx; a.gy = g.gy;
+        a.magic_gx = (unsigned)(((1ull << 32) + g.gx - 1) / g.gx); a.magic_gy = (unsigned)(((1ull << 32) + g.gy - 1) / g.gy);
         a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC ? g.per : 0;
         a.stats = stats;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
@@ -431,6 +453,19 @@ struct Ctx final : CtxBase {
         int dep = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
         const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
         int rc;
+        if constexpr (std::is_same<R, float>::value) {
+            if (use_push2 && dep == CPIC_DEPOSIT_WARP) {
+                // packed sqrt/div fast path only when qdt_2mc is a well-scaled normal number (or zero)
+                const float aq = fabsf((float)a.qdt_2mc);
+                const bool fd = push2_fastds && (aq == 0.f || (aq > 1e-12f && aq < 1e12f));
+                if (want_stats) rc = fma ? launch_push2<true, true, false>(a) : launch_push2<false, true, false>(a);
+                else if (fd) rc = fma ? launch_push2<true, false, true>(a) : launch_push2<false, false, true>(a);
+                else rc = fma ? launch_push2<true, false, false>(a) : launch_push2<false, false, false>(a);
+                cudaEventRecord(ev[1], stream);
+                ev_valid[0] = true;
+                return rc;
+            }
+        }
         if (dep == CPIC_DEPOSIT_ATOMIC) rc = fma ? launch_push<true, 1>(a) : launch_push<false, 1>(a);
         else if (dep == CPIC_DEPOSIT_ATOMIC_V4) rc = fma ? launch_push<true, 2>(a) : launch_push<false, 2>(a);
         else rc = fma ? launch_push<true, 3>(a) : launch_push<false, 3>(a);

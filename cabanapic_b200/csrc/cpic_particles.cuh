@@ -34,6 +34,7 @@ struct PushArgs {
     R* acc;        // [nc][12]
     R qdt_2mc, cdt_dx, cdt_dy, cdt_dz, qsp;
     int nx, ny, nz, ng, gx, gy;
+    unsigned magic_gx, magic_gy;   // ceil(2^32 / gx), ceil(2^32 / gy)
     int periodic;     // bit a: wrap along axis a (0 x, 1 y, 2 z); cleared: the particle stays in the ghost cell
     int dep_thresh;   // mixed warps: runs at least this long are warp-reduced, shorter ones use direct atomics
     int dep_rounds;   // mixed warps: at most this many peel rounds before falling back to direct atomics
@@ -222,9 +223,13 @@ template <class R>
 __device__ __forceinline__ int cross_face(int& ii, int axis, R dirv, const PushArgs<R>& a) {
     int face = axis;
     if (dirv > 0) face += 3;
-    int iy = ii / a.gx;
+    // RANK_TO_INDEX (src/types.h:184-193) with the two divisions done by multiply-high with the
+    // host-computed ceil(2^32/d) and one correction step (exact for 0 <= ii < 2^31, d < 2^16)
+    int iy = (int)__umulhi((unsigned)ii, a.magic_gx);
+    if (iy * a.gx > ii) --iy;
     int ix = ii - iy * a.gx;
-    int iz = iy / a.gy;
+    int iz = (int)__umulhi((unsigned)iy, a.magic_gy);
+    if (iz * a.gy > iy) --iz;
     iy -= iz * a.gy;
     if (face == 0) ix--;
     if (face == 1) iy--;
@@ -293,18 +298,18 @@ __device__ __forceinline__ void load_record(const R* __restrict__ ip, int ii, R 
 constexpr int PUSH_WARPS = 8;          // warps per block
 constexpr int MOVER_CAP = 64;          // per-warp list capacity (drained at >= 32)
 
-template <class R>
+template <class R, int CAP = MOVER_CAP>
 struct WarpMoverList {
-    R x[MOVER_CAP], y[MOVER_CAP], z[MOVER_CAP], rx[MOVER_CAP], ry[MOVER_CAP], rz[MOVER_CAP], q[MOVER_CAP];
-    int cell[MOVER_CAP];
-    unsigned idx[MOVER_CAP];   // global particle index (< 2^31)
+    R x[CAP], y[CAP], z[CAP], rx[CAP], ry[CAP], rz[CAP], q[CAP];
+    int cell[CAP];
+    unsigned idx[CAP];   // global particle index (< 2^31)
 };
 
 // Drain list entries [first, first+32) (lanes beyond `count` idle).  Reference: move_p,
 // src/move_p.h:93-371 -- streak, deposit into the current cell, then either stop (end of
 // track) or cross the face into the neighbour and continue.
-template <class R, bool FMA, int DEPOSIT, bool STATS>
-__device__ __forceinline__ void drain_movers(const PushArgs<R>& a, WarpMoverList<R>& ml, int first, int count,
+template <class R, bool FMA, int DEPOSIT, bool STATS, class List>
+__device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int first, int count,
                                              int lane, unsigned long long& n_cross, unsigned long long (&n_wrap)[6]) {
     const int m = first + lane;
     if (lane < count) {
