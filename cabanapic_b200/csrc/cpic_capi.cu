@@ -39,6 +39,8 @@ struct CtxBase {
     cudaEvent_t ev[8]{};   // 0/1 push, 2/3 sort, 4/5 field side, 6/7 step
     bool ev_valid[4] = {false, false, false, false};
     bool want_stats = false;
+    bool want_hist = false;    // set by cpic_step before a push that is followed by a sort
+    bool hist_valid = false;   // cell_count holds the histogram of the current cells (from the last push)
     // opt-in per-phase profile of cpic_step: 5 events per step (start, after sort, before push,
     // after push, end) on the context's stream
     bool prof_on = false;
@@ -149,6 +151,7 @@ struct Ctx final : CtxBase {
         if (const char* e = getenv("CPIC_PUSH_GRID")) push_grid = atoi(e);
         if (const char* e = getenv("CPIC_PUSH_V1")) use_push2 = atoi(e) == 0;
         if (const char* e = getenv("CPIC_PUSH2_FASTDS")) push2_fastds = atoi(e) != 0;
+        if (const char* e = getenv("CPIC_SCATTER_V1")) use_scatter2 = atoi(e) == 0;
         if (const char* e = getenv("CPIC_DEP_THRESH")) dep_thresh = atoi(e);
         if (const char* e = getenv("CPIC_DEP_ROUNDS")) dep_rounds = atoi(e);
         nc_pad = (g.nc + 63) / 64 * 64;
@@ -192,6 +195,7 @@ struct Ctx final : CtxBase {
             if ((rc = cuda(cudaMemcpyAsync(dst[k], m[k], (size_t)n * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D particles"))) return rc;
         if ((rc = cuda(cudaMemcpyAsync(p.cell, cell, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream), "H2D cell"))) return rc;
         np = n;
+        hist_valid = false;
         // bounds-check the cell indices once on upload (would have caught decks/2stream-short.cxx)
         cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
         if (n > 0) {
@@ -303,6 +307,7 @@ struct Ctx final : CtxBase {
             mig_cap = 2 * cap_send;
         }
         *n_lo = *n_hi = 0;
+        hist_valid = false;
         if (np == 0) return CPIC_OK;
         cudaMemsetAsync(mig_counters, 0, 8 * sizeof(unsigned), stream);
         const int plane = g.gx * g.gy;
@@ -329,6 +334,7 @@ struct Ctx final : CtxBase {
         if (n < 0 || n > cap_buf) return fail(CPIC_E_INVALID, "append_particles_device: bad count");
         if (np + n > cap) return fail(CPIC_E_CAPACITY, "append_particles_device: %lld + %lld particles exceed capacity %lld", np, n, cap);
         if (n == 0) return CPIC_OK;
+        hist_valid = false;
         SendBuf<R> b = carve_sendbuf<R>(const_cast<void*>(buf), cap_buf);
         Particles<R>& p = P[cur];
         R* dst[7] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w};
@@ -422,9 +428,14 @@ struct Ctx final : CtxBase {
     }
     // second-generation float kernel (packed FP32x2, two particles per thread); deposit mode WARP only
     bool use_push2 = true, push2_fastds = true;
+    bool use_scatter2 = true;
     template <bool FMA, bool ST, bool FD>
     int launch_push2(const PushArgs<float>& a) {
-        auto kern = k_push2<FMA, ST, FD>;
+        return a.hist ? launch_push2h<FMA, ST, FD, true>(a) : launch_push2h<FMA, ST, FD, false>(a);
+    }
+    template <bool FMA, bool ST, bool FD, bool H>
+    int launch_push2h(const PushArgs<float>& a) {
+        auto kern = k_push2<FMA, ST, FD, H>;
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PUSH2_WARPS * 32, 0);
         if (per_sm < 1) per_sm = 1;
@@ -447,6 +458,16 @@ struct Ctx final : CtxBase {
         a.magic_gx = (unsigned)(((1ull << 32) + g.gx - 1) / g.gx); a.magic_gy = (unsigned)(((1ull << 32) + g.gy - 1) / g.gy);
         a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC ? g.per : 0;
         a.stats = stats;
+        a.hist = nullptr;
+        hist_valid = false;
+        const int dep_mode = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
+        const bool p2 = std::is_same<R, float>::value && use_push2 && dep_mode == CPIC_DEPOSIT_WARP;
+        if (want_hist && prm.enable_sort && p2) {      // the next step sorts: let k_push2 count the new cells
+            cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
+            a.hist = cell_count;
+            hist_valid = true;
+        }
+        want_hist = false;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
         cudaEventRecord(ev[0], stream);
@@ -504,12 +525,16 @@ struct Ctx final : CtxBase {
         if (np == 0) return CPIC_OK;
         int rc;
         cudaEventRecord(ev[2], stream);
-        cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
-        cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
-        k_cell_histogram<<<blocks_for(np), 256, 0, stream>>>(P[cur].cell, np, g.nc, cell_count, bad);
-        if ((rc = check_launch("k_cell_histogram"))) return rc;
+        if (!hist_valid) {
+            cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
+            cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
+            k_cell_histogram<<<blocks_for(np), 256, 0, stream>>>(P[cur].cell, np, g.nc, cell_count, bad);
+            if ((rc = check_launch("k_cell_histogram"))) return rc;
+        }
+        hist_valid = false;
         if ((rc = scan_cells())) return rc;
-        k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
+        if (use_scatter2) k_sort_scatter2<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
+        else k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
         if ((rc = check_launch("k_sort_scatter"))) return rc;
         cur ^= 1;
         cudaEventRecord(ev[3], stream);
@@ -521,6 +546,7 @@ struct Ctx final : CtxBase {
         if (a.count < 0 || a.count > cap) return fail(CPIC_E_CAPACITY, "init_uniform_plasma: %lld particles exceed capacity %lld", a.count, cap);
         if (a.gnx != g.nx || a.gny != g.ny) return fail(CPIC_E_INVALID, "init_uniform_plasma: x/y extents must equal the context's");
         np = a.count;
+        hist_valid = false;
         if (np == 0) return CPIC_OK;
         k_init_uniform_plasma<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], a);
         return check_launch("k_init_uniform_plasma");
@@ -701,6 +727,7 @@ int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_
         if (!rc) rc = c->load_interpolator();
         if (!rc) rc = c->clear_accumulator();
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 2], c->stream);
+        c->want_hist = sort_interval > 0 && (s + 1) % sort_interval == 0;   // the next step starts with a sort
         if (!rc) rc = c->push(*k);
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 3], c->stream);
         if (!rc) rc = c->unload_accumulator(*k);
@@ -755,6 +782,7 @@ int cpic_set_num_particles(cpic_ctx* ctx, int64_t n) {
     CTX_OR_FAIL(ctx);
     if (n < 0 || n > c->prm.max_particles) return c->fail(CPIC_E_CAPACITY, "set_num_particles: %lld out of range", (long long)n);
     c->np = n;
+    c->hist_valid = false;
     return CPIC_OK;
 }
 

@@ -39,6 +39,7 @@ struct PushArgs {
     int dep_thresh;   // mixed warps: runs at least this long are warp-reduced, shorter ones use direct atomics
     int dep_rounds;   // mixed warps: at most this many peel rounds before falling back to direct atomics
     unsigned long long* stats;  // optional: [0] movers [1] crossings [2..7] wraps per face
+    unsigned* hist;             // optional: per-cell count of the particles' NEW cells (feeds the next sort)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -339,6 +340,7 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
         const long long pn = ml.idx[m];
         a.p.dx[pn] = px; a.p.dy[pn] = py; a.p.dz[pn] = pz;
         if (c != c_in) a.p.cell[pn] = c;
+        if (a.hist) atomicAdd(a.hist + c, 1u);
     }
     __syncwarp();
 }

@@ -110,4 +110,31 @@ __global__ void __launch_bounds__(256) k_sort_scatter(Particles<R> src, Particle
     dst.w[d] = src.w[n]; dst.cell[d] = c;
 }
 
+// Second-generation scatter.  The first one is latency-bound (DRAM at 37 %, profiles/r01_sort_128cube_ncu.md):
+// per warp one dependent chain  cell load -> cursor atomic -> payload loads -> stores.  Here the eight
+// member loads are issued up front into registers, so the atomic's round trip overlaps them and only
+// the stores wait for it.
+template <class R>
+__global__ void __launch_bounds__(256) k_sort_scatter2(Particles<R> src, Particles<R> dst, long long np,
+                                                       unsigned* __restrict__ cursor) {
+    const long long n = blockIdx.x * 256LL + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = n < np;
+    int c = -1 - lane;
+    R v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, v6 = 0;
+    if (valid) {
+        c = src.cell[n];
+        v0 = src.dx[n]; v1 = src.dy[n]; v2 = src.dz[n]; v3 = src.ux[n]; v4 = src.uy[n]; v5 = src.uz[n]; v6 = src.w[n];
+    }
+    int rank, head_lane;
+    const int len = run_length_at_head(c, lane, rank, head_lane);
+    unsigned base = 0;
+    if (len > 0 && valid) base = atomicAdd(cursor + c, (unsigned)len);
+    base = __shfl_sync(0xffffffffu, base, head_lane);
+    if (!valid) return;
+    const long long d = (long long)base + rank;
+    dst.dx[d] = v0; dst.dy[d] = v1; dst.dz[d] = v2; dst.ux[d] = v3; dst.uy[d] = v4; dst.uz[d] = v5; dst.w[d] = v6;
+    dst.cell[d] = c;
+}
+
 }  // namespace cpic
