@@ -198,7 +198,8 @@ def run_ours(args):
     d = decks.uniform_plasma(nx, ny, nz, nppc)
     k, _, we = d.consts()
     n_total = d.num_particles
-    sort_interval = args.sort_interval if args.sort_interval is not None else 1
+    # measured at C5 (profiles/r01_bench_n1_sort_interval_*.log): 2 -> 43.2, 4 -> 38.0, 6 -> 36.9, 8 -> 35.8 ms/step
+    sort_interval = args.sort_interval if args.sort_interval is not None else 8
     fp = cp.FP_CONTRACT if args.fp == "contract" else cp.FP_STRICT
 
     if world > 1:
@@ -242,7 +243,7 @@ def run_ours(args):
     push_ms_per_launch = prof["push_ms"] / args.steps
     per_launch_particles = runner.local_particles()
     achieved = BYTES_PER_PARTICLE_STEP * per_launch_particles / (push_ms_per_launch * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_push (push + move_p + deposit)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_push2 (push + move_p + deposit)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
                 "particles_per_launch": per_launch_particles, "ms_per_launch": push_ms_per_launch,
@@ -278,7 +279,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": name, "particles": n_total, "cells": [nx, ny, nz], "ppc": nppc,
-                           "sort_interval": sort_interval, "fp_mode": args.fp, "deposit": "warp-aggregated",
+                           "sort_interval": sort_interval, "fp_mode": args.fp, "deposit": "shared-memory segmented sum + red.v4",
                            "parallelism": runner.describe(),
                            "l2": "inputs (>= 30 GB per GPU) exceed the 126 MB L2; no flush needed"},
                 "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,

@@ -436,8 +436,10 @@ struct Ctx final : CtxBase {
     template <bool FMA, bool ST, bool FD, bool H>
     int launch_push2h(const PushArgs<float>& a) {
         auto kern = k_push2<FMA, ST, FD, H>;
+        const size_t smem = sizeof(Push2Smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PUSH2_WARPS * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PUSH2_WARPS * 32, smem);
         if (per_sm < 1) per_sm = 1;
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device);
@@ -446,7 +448,7 @@ struct Ctx final : CtxBase {
         if (blocks > need) blocks = need;
         if (push_grid > 0) blocks = std::min<long long>(push_grid, need);
         volatile float one = 1.0f;     // a runtime value as far as the compiler is concerned (cpic_push2.cuh)
-        kern<<<(unsigned)blocks, PUSH2_WARPS * 32, 0, stream>>>(a, one);
+        kern<<<(unsigned)blocks, PUSH2_WARPS * 32, smem, stream>>>(a, one);
         return check_launch("k_push2");
     }
     int push(const cpic_consts& k) override {
