@@ -25,6 +25,7 @@ SOLVER_EM, SOLVER_ES_1D = 0, 1
 BOUNDARY_REFLECT, BOUNDARY_PERIODIC = 0, 1
 FP_STRICT, FP_CONTRACT = 0, 1
 DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_ATOMIC_V4, DEPOSIT_WARP = 0, 1, 2, 3
+SORT_FUSED = -1      # cpic_step sort_interval: keep the store cell-ordered with the reordering push
 
 ERROR_NAMES = {-1: "CPIC_E_INVALID", -2: "CPIC_E_CUDA", -3: "CPIC_E_NOMEM", -4: "CPIC_E_CAPACITY",
                -5: "CPIC_E_BAD_CELL", -6: "CPIC_E_UNSUPPORTED"}
@@ -111,6 +112,7 @@ def lib() -> C.CDLL:
             "cpic_update_ghosts": [vp, C.c_int],
             "cpic_step": [vp, C.POINTER(Consts), i64, i32, vp],
             "cpic_sort_particles": [vp],
+            "cpic_push_reorder": [vp, C.POINTER(Consts)],
             "cpic_init_uniform_plasma": [vp, i64, i64, i32, i32, i32, i32, i32, C.c_uint64, dbl, dbl, dbl, dbl],
             "cpic_enable_push_stats": [vp, i32],
             "cpic_push_stats_get": [vp, C.POINTER(PushStats)],
@@ -142,7 +144,7 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
             "cpic_upload_accumulators", "cpic_download_accumulators", "cpic_load_interpolator_array",
             "cpic_initialize_interpolator", "cpic_clear_accumulator_array", "cpic_push", "cpic_contribute",
             "cpic_unload_accumulator_array", "cpic_advance_b", "cpic_advance_e", "cpic_uncenter_particles",
-            "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_sort_particles", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
+            "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_sort_particles", "cpic_push_reorder", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
             "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
             "cpic_set_axis_periodic", "cpic_advance_b_stencil", "cpic_advance_e_stencil", "cpic_extract_z_leavers", "cpic_append_particles_device",
             "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile"]
@@ -293,6 +295,10 @@ class Context:
 
     def sort_particles(self):
         self._ck(self.L.cpic_sort_particles(self.h))
+
+    def push_reorder(self, k: Consts):
+        """cpic_push + the cell ordering of the store in one pass (include/cabanapic_b200.h)."""
+        self._ck(self.L.cpic_push_reorder(self.h, C.byref(k)))
 
     def init_uniform_plasma(self, first, count, gnx, gny, gnz, nppc, z0=0, seed=12345, vth=(0.1, 0.1, 0.1),
                             weight=1.0):

@@ -41,6 +41,7 @@ struct CtxBase {
     bool want_stats = false;
     bool want_hist = false;    // set by cpic_step before a push that is followed by a sort
     bool hist_valid = false;   // cell_count holds the histogram of the current cells (from the last push)
+    bool cursor_valid = false; // cell_count holds the exclusive scan of that histogram (ready for a reordering push)
     // opt-in per-phase profile of cpic_step: 5 events per step (start, after sort, before push,
     // after push, end) on the context's stream
     bool prof_on = false;
@@ -83,6 +84,8 @@ struct CtxBase {
     virtual int energies_async(double* dev_out2) = 0;
     virtual int update_ghosts(int which) = 0;
     virtual int sort() = 0;
+    virtual int push_reorder(const cpic_consts& k) = 0;
+    virtual int prepare_reorder() = 0;
     virtual int init_uniform(const UniformPlasmaArgs& a) = 0;
     virtual int device_ptr(int which, void** ptr, int64_t* count, int64_t* stride) = 0;
     virtual int fold_phase(int phase) = 0;
@@ -108,6 +111,7 @@ struct Ctx final : CtxBase {
     R* interp = nullptr;       // nc * S
     R* acc = nullptr;          // nc * 12
     unsigned* cell_count = nullptr;   // nc (+ scan scratch)
+    unsigned* cell_count2 = nullptr;  // nc: the histogram the reordering push writes while it consumes cell_count
     unsigned* scan_l1 = nullptr;
     unsigned* scan_l2 = nullptr;
     long long n_l1 = 0, n_l2 = 0;
@@ -120,7 +124,7 @@ struct Ctx final : CtxBase {
             cudaSetDevice(prm.device);
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(fields); cudaFree(interp); cudaFree(acc);
-            cudaFree(cell_count); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists);
+            cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists);
             if (own_stream && stream) cudaStreamDestroy(stream);
         }
     }
@@ -173,6 +177,7 @@ struct Ctx final : CtxBase {
             n_l2 = (n_l1 + SCAN_TILE - 1) / SCAN_TILE;
             if (n_l2 > SCAN_TILE) return fail(CPIC_E_INVALID, "grid too large for the 3-level cell scan");
             if ((rc = cuda(cudaMalloc(&cell_count, (size_t)g.nc * sizeof(unsigned)), "cudaMalloc(cell_count)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&cell_count2, (size_t)g.nc * sizeof(unsigned)), "cudaMalloc(cell_count2)"))) return rc;
             if ((rc = cuda(cudaMalloc(&scan_l1, (size_t)n_l1 * sizeof(unsigned)), "cudaMalloc"))) return rc;
             if ((rc = cuda(cudaMalloc(&scan_l2, (size_t)n_l2 * sizeof(unsigned)), "cudaMalloc"))) return rc;
         }
@@ -195,7 +200,7 @@ struct Ctx final : CtxBase {
             if ((rc = cuda(cudaMemcpyAsync(dst[k], m[k], (size_t)n * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D particles"))) return rc;
         if ((rc = cuda(cudaMemcpyAsync(p.cell, cell, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream), "H2D cell"))) return rc;
         np = n;
-        hist_valid = false;
+        hist_valid = false; cursor_valid = false;
         // bounds-check the cell indices once on upload (would have caught decks/2stream-short.cxx)
         cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
         if (n > 0) {
@@ -307,7 +312,7 @@ struct Ctx final : CtxBase {
             mig_cap = 2 * cap_send;
         }
         *n_lo = *n_hi = 0;
-        hist_valid = false;
+        hist_valid = false; cursor_valid = false;
         if (np == 0) return CPIC_OK;
         cudaMemsetAsync(mig_counters, 0, 8 * sizeof(unsigned), stream);
         const int plane = g.gx * g.gy;
@@ -334,7 +339,7 @@ struct Ctx final : CtxBase {
         if (n < 0 || n > cap_buf) return fail(CPIC_E_INVALID, "append_particles_device: bad count");
         if (np + n > cap) return fail(CPIC_E_CAPACITY, "append_particles_device: %lld + %lld particles exceed capacity %lld", np, n, cap);
         if (n == 0) return CPIC_OK;
-        hist_valid = false;
+        hist_valid = false; cursor_valid = false;
         SendBuf<R> b = carve_sendbuf<R>(const_cast<void*>(buf), cap_buf);
         Particles<R>& p = P[cur];
         R* dst[7] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w};
@@ -433,9 +438,11 @@ struct Ctx final : CtxBase {
     int launch_push2(const PushArgs<float>& a) {
         return a.hist ? launch_push2h<FMA, ST, FD, true>(a) : launch_push2h<FMA, ST, FD, false>(a);
     }
-    template <bool FMA, bool ST, bool FD, bool H>
+    template <bool FMA, bool ST, bool FD>
+    int launch_push2r(const PushArgs<float>& a) { return launch_push2h<FMA, ST, FD, true, true>(a); }
+    template <bool FMA, bool ST, bool FD, bool H, bool RE = false>
     int launch_push2h(const PushArgs<float>& a) {
-        auto kern = k_push2<FMA, ST, FD, H>;
+        auto kern = k_push2<FMA, ST, FD, H, RE>;
         const size_t smem = sizeof(Push2Smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
@@ -451,8 +458,62 @@ struct Ctx final : CtxBase {
         kern<<<(unsigned)blocks, PUSH2_WARPS * 32, smem, stream>>>(a, one);
         return check_launch("k_push2");
     }
-    int push(const cpic_consts& k) override {
+    // The reordering push (cpic_push2.cuh, REORD): cpic_push + the cell ordering of the particle store in one
+    // pass.  prepare_reorder() makes cell_count the exclusive scan of the current cells' histogram (from the
+    // previous reordering push when there was one); push_reorder() consumes it.
+    bool can_reorder() const {
+        const int dep = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
+        return std::is_same<R, float>::value && use_push2 && prm.enable_sort && dep == CPIC_DEPOSIT_WARP;
+    }
+    int prepare_reorder() override {
+        if (!prm.enable_sort) return fail(CPIC_E_INVALID, "push_reorder: context was created with enable_sort=0");
+        if (np == 0 || cursor_valid) return CPIC_OK;
+        int rc;
+        if (!hist_valid) {
+            cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
+            cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
+            k_cell_histogram<<<blocks_for(np), 256, 0, stream>>>(P[cur].cell, np, g.nc, cell_count, bad);
+            if ((rc = check_launch("k_cell_histogram"))) return rc;
+        }
+        hist_valid = false;
+        if ((rc = scan_cells())) return rc;
+        cursor_valid = true;
+        return CPIC_OK;
+    }
+    int push_reorder(const cpic_consts& k) override {
+        if (!can_reorder()) {          // double / other deposit modes: a counting sort, then the in-place push
+            int rc = sort();
+            return rc ? rc : push(k);
+        }
         if (np == 0) return CPIC_OK;
+        int rc;
+        if ((rc = prepare_reorder())) return rc;
+        if constexpr (std::is_same<R, float>::value) {
+            PushArgs<float> a = push_args(k);
+            a.dst = P[cur ^ 1];
+            a.cursor = cell_count;
+            a.hist = cell_count2;
+            cudaMemsetAsync(cell_count2, 0, (size_t)g.nc * sizeof(unsigned), stream);
+            if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
+            cudaEventRecord(ev[0], stream);
+            const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
+            const float aq = fabsf((float)a.qdt_2mc);
+            const bool fd = push2_fastds && (aq == 0.f || (aq > 1e-12f && aq < 1e12f));
+            if (want_stats) rc = fma ? launch_push2r<true, true, false>(a) : launch_push2r<false, true, false>(a);
+            else if (fd) rc = fma ? launch_push2r<true, false, true>(a) : launch_push2r<false, false, true>(a);
+            else rc = fma ? launch_push2r<true, false, false>(a) : launch_push2r<false, false, false>(a);
+            cudaEventRecord(ev[1], stream);
+            ev_valid[0] = true;
+            if (rc) return rc;
+            cur ^= 1;
+            std::swap(cell_count, cell_count2);      // cell_count: histogram of the cells the particles are in now
+            hist_valid = true;
+            cursor_valid = false;
+            want_hist = false;
+        }
+        return CPIC_OK;
+    }
+    PushArgs<R> push_args(const cpic_consts& k) {
         PushArgs<R> a;
         a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
         a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
@@ -461,7 +522,22 @@ struct Ctx final : CtxBase {
         a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC ? g.per : 0;
         a.stats = stats;
         a.hist = nullptr;
-        hist_valid = false;
+        a.dst = P[cur]; a.cursor = nullptr;
+        a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
+        return a;
+    }
+    int push(const cpic_consts& k) override {
+        if (np == 0) return CPIC_OK;
+        PushArgs<R> a;
+        a.dst = P[cur]; a.cursor = nullptr;
+        a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
+        a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
+        a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.ng = g.ng; a.gx = g.gx; a.gy = g.gy;
+        a.magic_gx = (unsigned)(((1ull << 32) + g.gx - 1) / g.gx); a.magic_gy = (unsigned)(((1ull << 32) + g.gy - 1) / g.gy);
+        a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC ? g.per : 0;
+        a.stats = stats;
+        a.hist = nullptr;
+        hist_valid = false; cursor_valid = false;
         const int dep_mode = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
         const bool p2 = std::is_same<R, float>::value && use_push2 && dep_mode == CPIC_DEPOSIT_WARP;
         if (want_hist && prm.enable_sort && p2) {      // the next step sorts: let k_push2 count the new cells
@@ -533,7 +609,7 @@ struct Ctx final : CtxBase {
             k_cell_histogram<<<blocks_for(np), 256, 0, stream>>>(P[cur].cell, np, g.nc, cell_count, bad);
             if ((rc = check_launch("k_cell_histogram"))) return rc;
         }
-        hist_valid = false;
+        hist_valid = false; cursor_valid = false;
         if ((rc = scan_cells())) return rc;
         if (use_scatter2) k_sort_scatter2<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
         else k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
@@ -548,7 +624,7 @@ struct Ctx final : CtxBase {
         if (a.count < 0 || a.count > cap) return fail(CPIC_E_CAPACITY, "init_uniform_plasma: %lld particles exceed capacity %lld", a.count, cap);
         if (a.gnx != g.nx || a.gny != g.ny) return fail(CPIC_E_INVALID, "init_uniform_plasma: x/y extents must equal the context's");
         np = a.count;
-        hist_valid = false;
+        hist_valid = false; cursor_valid = false;
         if (np == 0) return CPIC_OK;
         k_init_uniform_plasma<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], a);
         return check_launch("k_init_uniform_plasma");
@@ -669,6 +745,7 @@ int cpic_advance_e(cpic_ctx* ctx, double px, double py, double pz, double dt_eps
 int cpic_uncenter_particles(cpic_ctx* ctx, double qdt_2mc) { CTX_OR_FAIL(ctx); return c->uncenter(qdt_2mc); }
 int cpic_update_ghosts(cpic_ctx* ctx, int which) { CTX_OR_FAIL(ctx); return c->update_ghosts(which); }
 int cpic_sort_particles(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->sort(); }
+int cpic_push_reorder(cpic_ctx* ctx, const cpic_consts* k) { CTX_OR_FAIL(ctx); if (!k) return c->fail(CPIC_E_INVALID, "push_reorder: null consts"); return c->push_reorder(*k); }
 
 int cpic_init_uniform_plasma(cpic_ctx* ctx, int64_t first, int64_t count, int32_t gnx, int32_t gny, int32_t gnz,
                              int32_t nppc, int32_t z0, uint64_t seed, double vthx, double vthy, double vthz,
@@ -703,7 +780,7 @@ int cpic_energies(cpic_ctx* ctx, double* e_energy, double* b_energy) {
 
 int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, double* energies) {
     CTX_OR_FAIL(ctx);
-    if (!k || nsteps < 0) return c->fail(CPIC_E_INVALID, "step: bad arguments");
+    if (!k || nsteps < 0 || sort_interval < CPIC_SORT_FUSED) return c->fail(CPIC_E_INVALID, "step: bad arguments");
     int rc = CPIC_OK;
     double* en = nullptr;
     if (energies && nsteps > 0)
@@ -724,13 +801,15 @@ int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_
     for (int64_t s = 0; s < nsteps && !rc; ++s) {
         // example/example.cpp:221-266, plus the optional sort of :224-228
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 0], c->stream);
-        if (sort_interval > 0 && s % sort_interval == 0) rc = c->sort();
+        const bool fused = sort_interval == CPIC_SORT_FUSED;
+        if (fused) rc = c->prepare_reorder();        // histogram (first step only) + scan of the cell counts
+        else if (sort_interval > 0 && s % sort_interval == 0) rc = c->sort();
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 1], c->stream);
         if (!rc) rc = c->load_interpolator();
         if (!rc) rc = c->clear_accumulator();
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 2], c->stream);
         c->want_hist = sort_interval > 0 && (s + 1) % sort_interval == 0;   // the next step starts with a sort
-        if (!rc) rc = c->push(*k);
+        if (!rc) rc = fused ? c->push_reorder(*k) : c->push(*k);
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 3], c->stream);
         if (!rc) rc = c->unload_accumulator(*k);
         if (!rc) rc = c->advance_b(hx, hy, hz);
@@ -784,7 +863,7 @@ int cpic_set_num_particles(cpic_ctx* ctx, int64_t n) {
     CTX_OR_FAIL(ctx);
     if (n < 0 || n > c->prm.max_particles) return c->fail(CPIC_E_CAPACITY, "set_num_particles: %lld out of range", (long long)n);
     c->np = n;
-    c->hist_valid = false;
+    c->hist_valid = false; c->cursor_valid = false;
     return CPIC_OK;
 }
 

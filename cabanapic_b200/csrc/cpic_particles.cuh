@@ -40,6 +40,10 @@ struct PushArgs {
     int dep_rounds;   // mixed warps: at most this many peel rounds before falling back to direct atomics
     unsigned long long* stats;  // optional: [0] movers [1] crossings [2..7] wraps per face
     unsigned* hist;             // optional: per-cell count of the particles' NEW cells (feeds the next sort)
+    // reordering push (k_push2<..., REORD>): the advanced particles are written to `dst`, each to a slot of
+    // the segment of the cell it occupied when the step began (cursor = exclusive scan of that histogram)
+    Particles<R> dst;
+    unsigned* cursor;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -309,7 +313,8 @@ struct WarpMoverList {
 // Drain list entries [first, first+32) (lanes beyond `count` idle).  Reference: move_p,
 // src/move_p.h:93-371 -- streak, deposit into the current cell, then either stop (end of
 // track) or cross the face into the neighbour and continue.
-template <class R, bool FMA, int DEPOSIT, bool STATS, class List>
+// OUTOFPLACE: the list's idx are slots of a.dst (reordering push) and the cell is always written.
+template <class R, bool FMA, int DEPOSIT, bool STATS, class List, bool OUTOFPLACE = false>
 __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int first, int count,
                                              int lane, unsigned long long& n_cross, unsigned long long (&n_wrap)[6]) {
     const int m = first + lane;
@@ -338,9 +343,15 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
             }
         }
         const long long pn = ml.idx[m];
-        a.p.dx[pn] = px; a.p.dy[pn] = py; a.p.dz[pn] = pz;
-        if (c != c_in) a.p.cell[pn] = c;
-        if (a.hist) atomicAdd(a.hist + c, 1u);
+        (void)c_in;
+        if constexpr (OUTOFPLACE) {
+            a.dst.dx[pn] = px; a.dst.dy[pn] = py; a.dst.dz[pn] = pz; a.dst.cell[pn] = c;
+            atomicAdd(a.hist + c, 1u);
+        } else {
+            a.p.dx[pn] = px; a.p.dy[pn] = py; a.p.dz[pn] = pz;
+            if (c != c_in) a.p.cell[pn] = c;
+            if (a.hist) atomicAdd(a.hist + c, 1u);
+        }
     }
     __syncwarp();
 }

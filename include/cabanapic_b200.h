@@ -137,6 +137,7 @@ int  cpic_update_ghosts(cpic_ctx* ctx, int which /* 0: fold J, 1: copy J, 2: cop
  * device: no host synchronisation between steps.  sort_interval > 0 re-sorts the particles
  * by cell every that many steps (the step the reference left commented out,
  * example/example.cpp:224-228).  energies (optional, host) receives (e,b) after every step. */
+#define CPIC_SORT_FUSED (-1)   /* sort_interval: keep the store cell-ordered with cpic_push_reorder, no sort pass */
 int  cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, double* energies);
 
 /* Device-side Particle_Initializer for the synthetic uniform thermal plasma (the reference's
@@ -150,6 +151,14 @@ int  cpic_init_uniform_plasma(cpic_ctx* ctx, int64_t first, int64_t count, int32
 
 /* Cabana::sortByKey by Cell_Index (example/example.cpp:224-228). */
 int  cpic_sort_particles(cpic_ctx* ctx);
+/* push<> (src/push.h:7-300) and that sortByKey in ONE pass over the particles: the advanced particles are
+ * written to the second particle buffer, each into the segment of the cell it occupied when the call
+ * began, so the store the next step reads is cell-ordered up to the particles that changed cell in this
+ * one step; the call also produces the cell histogram the next call's segments come from.  Same
+ * per-particle results as cpic_push; the order of the particles in the store changes (as with any sort).
+ * float + CPIC_DEPOSIT_WARP/AUTO contexts with enable_sort; otherwise equal to cpic_sort_particles +
+ * cpic_push. */
+int  cpic_push_reorder(cpic_ctx* ctx, const cpic_consts* k);
 int  cpic_enable_push_stats(cpic_ctx* ctx, int32_t on);   /* count movers/crossings/wraps in cpic_push (off by default) */
 int  cpic_push_stats_get(cpic_ctx* ctx, cpic_push_stats* out);
 

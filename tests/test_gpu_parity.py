@@ -496,7 +496,7 @@ def test_slab_stepper_single_rank_equals_fused_step():
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-@pytest.mark.parametrize("interval", [1, 2, 3])
+@pytest.mark.parametrize("interval", [1, 2, 3, -1])
 def test_sorted_steps_match_unsorted_oracle(prec, interval):
     """cpic_step with the periodic sort switched on (the push hands the histogram of the new cells to
     the following counting sort; the float path uses the pair-wise scatter kernel) against the oracle,
@@ -528,3 +528,102 @@ def test_sorted_steps_match_unsorted_oracle(prec, interval):
     o1, o2 = canonical_order(p), canonical_order(ps)
     for n in PARTICLE_NAMES:
         assert np.array_equal(p[n][o1], ps[n][o2]), n
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+@pytest.mark.parametrize("fp", ["strict", "contract"])
+@pytest.mark.parametrize("grid", GRIDS)
+def test_push_reorder_teacher_forced(grid, fp, shuffle):
+    """cpic_push_reorder (push + cell ordering in one pass, float): three consecutive calls, each from the
+    oracle's inputs.  Bars: the particle multiset after every call is bit-identical to the oracle's push
+    (strict mode; contract: 2e-6), mover / crossing counts exact, accumulators to summation order, and the
+    store comes back ordered by the cell each particle occupied BEFORE that call (the segments come from the
+    previous call's histogram from the second call on)."""
+    nx, ny, nz = grid
+    s = random_state(nx, ny, nz, nppc=37, prec="f32", seed=5)
+    if shuffle:                                   # arbitrary input order: no cell runs for the claims to merge
+        perm = np.random.default_rng(1).permutation(s.np)
+        for n in PARTICLE_NAMES:
+            s.p[n][:] = s.p[n][perm]
+    k = consts_for(nx, ny, nz, "f32")
+    O = Restatement("f32")
+    m = cp()
+    with make_ctx(s, fp_mode=m.FP_CONTRACT if fp == "contract" else m.FP_STRICT) as c:
+        c.enable_push_stats(True)
+        for call in range(3):
+            old_cell = s.p["cell"].copy()
+            O.load_interpolator(s); c.load_interpolator_array()
+            O.clear_accumulator(s); c.clear_accumulator_array()
+            movers, crossings = O.push(s, k)
+            c.push_reorder(to_k(k))
+            p = c.download_particles()
+            assert len(p["cell"]) == s.np
+            a, b = canonical_order(p), canonical_order(s.p)
+            if fp == "strict":
+                for n in PARTICLE_NAMES:
+                    assert np.array_equal(p[n][a], s.p[n][b]), (call, n)
+                st = c.push_stats()
+                assert st["movers"] == movers and st["crossings"] == crossings and movers > 0
+                # order of the store = order of the cells before the call
+                before = np.empty(s.np, dtype=np.int64)
+                before[a] = old_cell[b]
+                assert np.all(np.diff(before) >= 0), call
+            else:
+                assert np.array_equal(np.sort(p["w"]), np.sort(s.p["w"]))
+                assert np.mean(p["cell"][a] == s.p["cell"][b]) > 0.995
+            assert acc_close(c.download_accumulators(), s.acc, "f32")
+            if fp == "contract":                  # keep the oracle and the device on the same inputs
+                c.upload_particles(s.p)
+
+
+def test_push_reorder_edge_cases_and_fallbacks():
+    """Odd / tiny / empty particle counts, a context without the second buffer, double precision
+    (= cpic_sort_particles + cpic_push), and mixing with the in-place push and the sort."""
+    m = cp()
+    k = consts_for(3, 3, 2, "f32")
+    O = Restatement("f32")
+    for npart in (0, 1, 2, 63, 64, 65, 129):
+        s = random_state(3, 3, 2, nppc=8, prec="f32", seed=3)
+        keep = np.random.default_rng(npart).permutation(s.np)[:npart]
+        from oracle.api import State
+        t = State(3, 3, 2, 1, npart, "f32")
+        for n in PARTICLE_NAMES:
+            t.p[n][:] = s.p[n][keep]
+        t.f[:] = s.f
+        with make_ctx(t) as c:
+            O.load_interpolator(t); c.load_interpolator_array()
+            O.clear_accumulator(t); c.clear_accumulator_array()
+            O.push(t, k); c.push_reorder(to_k(k))
+            c.sort_particles()                    # the pending histogram feeds a plain sort as well
+            p = c.download_particles()
+            a, b = canonical_order(p), canonical_order(t.p)
+            for n in PARTICLE_NAMES:
+                assert np.array_equal(p[n][a], t.p[n][b]), (npart, n)
+            assert np.all(np.diff(p["cell"]) >= 0)
+            assert acc_close(c.download_accumulators(), t.acc, "f32")
+            # and an in-place push afterwards still works on the reordered store
+            O.load_interpolator(t); c.load_interpolator_array()
+            O.clear_accumulator(t); c.clear_accumulator_array()
+            O.push(t, k); c.push(to_k(k))
+            O.load_interpolator(t); c.load_interpolator_array()
+            O.clear_accumulator(t); c.clear_accumulator_array()
+            O.push(t, k); c.push_reorder(to_k(k))
+            p = c.download_particles()
+            a, b = canonical_order(p), canonical_order(t.p)
+            for n in PARTICLE_NAMES:
+                assert np.array_equal(p[n][a], t.p[n][b]), (npart, n)
+    s = random_state(3, 3, 2, nppc=8, prec="f32", seed=3)
+    with make_ctx(s, enable_sort=False) as c:
+        with pytest.raises(m.CpicError):
+            c.push_reorder(to_k(k))
+    s = random_state(3, 3, 2, nppc=8, prec="f64", seed=3)
+    k = consts_for(3, 3, 2, "f64")
+    O = Restatement("f64")
+    with make_ctx(s) as c:
+        O.load_interpolator(s); c.load_interpolator_array()
+        O.clear_accumulator(s); c.clear_accumulator_array()
+        O.push(s, k); c.push_reorder(to_k(k))
+        p = c.download_particles()
+        a, b = canonical_order(p), canonical_order(s.p)
+        for n in PARTICLE_NAMES:
+            assert np.array_equal(p[n][a], s.p[n][b]), n
