@@ -102,11 +102,16 @@ template <class R>
 struct Ctx final : CtxBase {
     static constexpr int S = IpStride<R>::value;
     long long nc_pad = 0;
-    // particle store: two buffers (second only with enable_sort), members padded to 16 B multiples
+    // particle store: two buffers of records (second only with enable_sort), capacity a multiple of 64
     long long cap = 0;
     char* pbuf[2] = {nullptr, nullptr};
     Particles<R> P[2];
     int cur = 0;
+    // struct-of-arrays staging chunk for host transfers (the C ABI exchanges the eight members as separate
+    // arrays, like Cabana slices): 8 copies per chunk + one pack/unpack kernel, all on the context's stream
+    static constexpr long long XFER_CHUNK = 1ll << 23;
+    char* xfer = nullptr;
+    long long xfer_cap = 0;
     R* fields = nullptr;       // 9 * nc_pad
     R* interp = nullptr;       // nc * S
     R* acc = nullptr;          // nc * 12
@@ -123,7 +128,7 @@ struct Ctx final : CtxBase {
         if (stream || true) {
             cudaSetDevice(prm.device);
             for (auto& e : ev) if (e) cudaEventDestroy(e);
-            cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(fields); cudaFree(interp); cudaFree(acc);
+            cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer); cudaFree(fields); cudaFree(interp); cudaFree(acc);
             cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists);
             if (own_stream && stream) cudaStreamDestroy(stream);
         }
@@ -135,12 +140,10 @@ struct Ctx final : CtxBase {
         return f;
     }
 
-    void carve(int b) {
-        char* p = pbuf[b];
-        const long long stride_r = cap * (long long)sizeof(R), stride_i = cap * (long long)sizeof(int);
-        P[b].dx = (R*)p; p += stride_r; P[b].dy = (R*)p; p += stride_r; P[b].dz = (R*)p; p += stride_r;
-        P[b].ux = (R*)p; p += stride_r; P[b].uy = (R*)p; p += stride_r; P[b].uz = (R*)p; p += stride_r;
-        P[b].w = (R*)p; p += stride_r; P[b].cell = (int*)p; p += stride_i;
+    int ensure_xfer() {
+        if (xfer) return CPIC_OK;
+        xfer_cap = std::min<long long>(cap, XFER_CHUNK);
+        return cuda(cudaMalloc(&xfer, (size_t)xfer_cap * (7 * sizeof(R) + sizeof(int))), "cudaMalloc(transfer staging)");
     }
 
     int init() {
@@ -155,16 +158,15 @@ struct Ctx final : CtxBase {
         if (const char* e = getenv("CPIC_PUSH_GRID")) push_grid = atoi(e);
         if (const char* e = getenv("CPIC_PUSH_V1")) use_push2 = atoi(e) == 0;
         if (const char* e = getenv("CPIC_PUSH2_FASTDS")) push2_fastds = atoi(e) != 0;
-        if (const char* e = getenv("CPIC_SCATTER_V1")) use_scatter2 = atoi(e) == 0;
         if (const char* e = getenv("CPIC_DEP_THRESH")) dep_thresh = atoi(e);
         if (const char* e = getenv("CPIC_DEP_ROUNDS")) dep_rounds = atoi(e);
         nc_pad = (g.nc + 63) / 64 * 64;
         cap = (prm.max_particles + 63) / 64 * 64;
         if (cap < 64) cap = 64;
-        const size_t pbytes = (size_t)cap * (7 * sizeof(R) + sizeof(int));
+        const size_t pbytes = (size_t)cap * sizeof(PRec<R>);
         for (int b = 0; b < (prm.enable_sort ? 2 : 1); ++b) {
             if ((rc = cuda(cudaMalloc(&pbuf[b], pbytes), "cudaMalloc(particles)"))) return rc;
-            carve(b);
+            P[b].rec = reinterpret_cast<PRec<R>*>(pbuf[b]);
         }
         if ((rc = cuda(cudaMalloc(&fields, (size_t)nc_pad * F_N * sizeof(R)), "cudaMalloc(fields)"))) return rc;
         if ((rc = cuda(cudaMalloc(&interp, (size_t)g.nc * S * sizeof(R)), "cudaMalloc(interpolators)"))) return rc;
@@ -193,18 +195,23 @@ struct Ctx final : CtxBase {
     // ------------------------------------------------------------------ transfers
     int upload_particles(const void* const m[7], const int32_t* cell, long long n) override {
         if (n < 0 || n > cap) return fail(CPIC_E_CAPACITY, "upload_particles: %lld particles exceed capacity %lld", n, cap);
-        Particles<R>& p = P[cur];
-        R* dst[7] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w};
         int rc;
-        for (int k = 0; k < 7; ++k)
-            if ((rc = cuda(cudaMemcpyAsync(dst[k], m[k], (size_t)n * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D particles"))) return rc;
-        if ((rc = cuda(cudaMemcpyAsync(p.cell, cell, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream), "H2D cell"))) return rc;
+        if ((rc = ensure_xfer())) return rc;
+        cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
+        for (long long first = 0; first < n; first += xfer_cap) {
+            const long long cn = std::min(xfer_cap, n - first);
+            SendBuf<R> b = carve_sendbuf<R>(xfer, xfer_cap);
+            for (int k = 0; k < 7; ++k)
+                if ((rc = cuda(cudaMemcpyAsync(b.m[k], (const R*)m[k] + first, (size_t)cn * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D particles"))) return rc;
+            if ((rc = cuda(cudaMemcpyAsync(b.cell, cell + first, (size_t)cn * sizeof(int), cudaMemcpyHostToDevice, stream), "H2D cell"))) return rc;
+            k_pack_records<R><<<blocks_for(cn), 256, 0, stream>>>(P[cur], first, b, cn);
+            if ((rc = check_launch("k_pack_records"))) return rc;
+        }
         np = n;
         hist_valid = false; cursor_valid = false;
         // bounds-check the cell indices once on upload (would have caught decks/2stream-short.cxx)
-        cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
         if (n > 0) {
-            k_check_cells<<<blocks_for(n), 256, 0, stream>>>(p.cell, n, g.nc, bad);
+            k_check_cells<R><<<blocks_for(n), 256, 0, stream>>>(P[cur], n, g.nc, bad);
             if ((rc = check_launch("k_check_cells"))) return rc;
         }
         unsigned nbad = 0;
@@ -215,12 +222,17 @@ struct Ctx final : CtxBase {
     }
     int download_particles(void* const m[7], int32_t* cell, long long capacity, long long* n_out) override {
         if (capacity < np) return fail(CPIC_E_CAPACITY, "download_particles: buffer holds %lld, need %lld", capacity, np);
-        Particles<R>& p = P[cur];
-        R* src[7] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w};
         int rc;
-        for (int k = 0; k < 7; ++k)
-            if (m[k] && (rc = cuda(cudaMemcpyAsync(m[k], src[k], (size_t)np * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H particles"))) return rc;
-        if (cell && (rc = cuda(cudaMemcpyAsync(cell, p.cell, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H cell"))) return rc;
+        if ((rc = ensure_xfer())) return rc;
+        for (long long first = 0; first < np; first += xfer_cap) {
+            const long long cn = std::min(xfer_cap, np - first);
+            SendBuf<R> b = carve_sendbuf<R>(xfer, xfer_cap);
+            k_unpack_records<R><<<blocks_for(cn), 256, 0, stream>>>(P[cur], first, b, cn);
+            if ((rc = check_launch("k_unpack_records"))) return rc;
+            for (int k = 0; k < 7; ++k)
+                if (m[k] && (rc = cuda(cudaMemcpyAsync((R*)m[k] + first, b.m[k], (size_t)cn * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H particles"))) return rc;
+            if (cell && (rc = cuda(cudaMemcpyAsync(cell + first, b.cell, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H cell"))) return rc;
+        }
         if (n_out) *n_out = np;
         return cuda(cudaStreamSynchronize(stream), "download_particles");
     }
@@ -341,12 +353,9 @@ struct Ctx final : CtxBase {
         if (n == 0) return CPIC_OK;
         hist_valid = false; cursor_valid = false;
         SendBuf<R> b = carve_sendbuf<R>(const_cast<void*>(buf), cap_buf);
-        Particles<R>& p = P[cur];
-        R* dst[7] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w};
+        k_pack_records<R><<<blocks_for(n), 256, 0, stream>>>(P[cur], np, b, n);
         int rc;
-        for (int k = 0; k < 7; ++k)
-            if ((rc = cuda(cudaMemcpyAsync(dst[k] + np, b.m[k], (size_t)n * sizeof(R), cudaMemcpyDeviceToDevice, stream), "D2D append"))) return rc;
-        if ((rc = cuda(cudaMemcpyAsync(p.cell + np, b.cell, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, stream), "D2D append"))) return rc;
+        if ((rc = check_launch("k_pack_records"))) return rc;
         np += n;
         return CPIC_OK;
     }
@@ -433,7 +442,6 @@ struct Ctx final : CtxBase {
     }
     // second-generation float kernel (packed FP32x2, two particles per thread); deposit mode WARP only
     bool use_push2 = true, push2_fastds = true;
-    bool use_scatter2 = true;
     template <bool FMA, bool ST, bool FD>
     int launch_push2(const PushArgs<float>& a) {
         return a.hist ? launch_push2h<FMA, ST, FD, true>(a) : launch_push2h<FMA, ST, FD, false>(a);
@@ -472,7 +480,7 @@ struct Ctx final : CtxBase {
         if (!hist_valid) {
             cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
             cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
-            k_cell_histogram<<<blocks_for(np), 256, 0, stream>>>(P[cur].cell, np, g.nc, cell_count, bad);
+            k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
             if ((rc = check_launch("k_cell_histogram"))) return rc;
         }
         hist_valid = false;
@@ -606,13 +614,12 @@ struct Ctx final : CtxBase {
         if (!hist_valid) {
             cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
             cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
-            k_cell_histogram<<<blocks_for(np), 256, 0, stream>>>(P[cur].cell, np, g.nc, cell_count, bad);
+            k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
             if ((rc = check_launch("k_cell_histogram"))) return rc;
         }
         hist_valid = false; cursor_valid = false;
         if ((rc = scan_cells())) return rc;
-        if (use_scatter2) k_sort_scatter2<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
-        else k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
+        k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
         if ((rc = check_launch("k_sort_scatter"))) return rc;
         cur ^= 1;
         cudaEventRecord(ev[3], stream);
@@ -631,9 +638,15 @@ struct Ctx final : CtxBase {
     }
 
     int device_ptr(int which, void** ptr, int64_t* count, int64_t* stride) override {
-        Particles<R>& p = P[cur];
-        void* pm[8] = {p.dx, p.dy, p.dz, p.ux, p.uy, p.uz, p.w, p.cell};
-        if (which >= 0 && which < 8) { *ptr = pm[which]; if (count) *count = cap; if (stride) *stride = 1; return CPIC_OK; }
+        // particle members live inside the records: member `which` of particle n is at ptr + n*stride reals
+        // (record order dx dy dz cell ux uy uz w; the cell is an int32/int64 in a real-sized slot)
+        if (which >= 0 && which < 8) {
+            static const int slot[8] = {0, 1, 2, 4, 5, 6, 7, 3};
+            *ptr = reinterpret_cast<R*>(P[cur].rec) + slot[which];
+            if (count) *count = cap;
+            if (stride) *stride = 8;
+            return CPIC_OK;
+        }
         if (which == 16) { *ptr = fields; if (count) *count = g.nc; if (stride) *stride = nc_pad; return CPIC_OK; }
         if (which == 17) { *ptr = interp; if (count) *count = g.nc; if (stride) *stride = S; return CPIC_OK; }
         if (which == 18) { *ptr = acc; if (count) *count = g.nc; if (stride) *stride = 12; return CPIC_OK; }

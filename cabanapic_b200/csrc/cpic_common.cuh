@@ -43,6 +43,42 @@ struct Fields {
     R* c[F_N];
 };
 
+// ---- particle store: an array of records ------------------------------------------------------------
+// One particle is one record of the reference's eight AoSoA members (src/types.h:31-58) in two 4-wide
+// halves: pos = (dx, dy, dz, cell) and mom = (ux, uy, uz, w).  In float that is 32 bytes = exactly one
+// DRAM/L2 sector, read with one 256-bit load (LDG.E.ENL2.256 on sm_100a) and -- the reason for this
+// layout -- written as ONE FULL sector wherever the particle lands, which is what lets the push and the
+// sort scatter particles into cell order at copy speed; the struct-of-arrays store this replaced turned
+// every moved particle into eight partial-sector writes (158 B/particle of DRAM traffic for 64 useful,
+// profiles/r01_push2_reorder_v1_256x256x32_ncu.md; tools/ubench/scatter_layout.cu).
+// The cell index travels in the bits of pos.w (int32 in float records, int64 in double records) and is
+// only ever moved, never used in arithmetic.
+template <class R> struct PHalf;
+template <> struct __align__(16) PHalf<float>  { float x, y, z, w; };
+template <> struct __align__(32) PHalf<double> { double x, y, z, w; };
+template <class R> struct PRec;
+template <> struct __align__(32) PRec<float>  { PHalf<float> pos, mom; };
+template <> struct __align__(64) PRec<double> { PHalf<double> pos, mom; };
+
+__device__ __forceinline__ float  cell_to_real(int c, float)  { return __int_as_float(c); }
+__device__ __forceinline__ double cell_to_real(int c, double) { return __longlong_as_double((long long)c); }
+__device__ __forceinline__ int real_to_cell(float v)  { return __float_as_int(v); }
+__device__ __forceinline__ int real_to_cell(double v) { return (int)__double_as_longlong(v); }
+
+template <class R>
+struct Particles {
+    PRec<R>* rec;
+    __device__ __forceinline__ int cell(long long n) const { return real_to_cell(rec[n].pos.w); }
+    __device__ __forceinline__ void store_pos(long long n, R x, R y, R z, int c) const {
+        PHalf<R> h; h.x = x; h.y = y; h.z = z; h.w = cell_to_real(c, R(0));
+        rec[n].pos = h;
+    }
+    __device__ __forceinline__ void store_mom(long long n, R ux, R uy, R uz, R w) const {
+        PHalf<R> h; h.x = ux; h.y = uy; h.z = uz; h.w = w;
+        rec[n].mom = h;
+    }
+};
+
 // Multiply-add under the context's floating-point policy.  This translation unit is
 // compiled with -fmad=false, so `a * b + c` below really is two roundings; the fused
 // form is only used when the caller asked for CPIC_FP_CONTRACT.

@@ -51,22 +51,24 @@ __global__ void __launch_bounds__(256) k_init_uniform_plasma(Particles<R> p, Uni
     unsigned ra[4], rb[4];
     philox4x32_10(k, 0u, a.seed, ra);
     philox4x32_10(k, 1u, a.seed, rb);
-    p.dx[n] = (R)(2.0 * u01(ra[0]) - 1.0);
-    p.dy[n] = (R)(2.0 * u01(ra[1]) - 1.0);
-    p.dz[n] = (R)(2.0 * u01(ra[2]) - 1.0);
+    PRec<R> r;
+    r.pos.x = (R)(2.0 * u01(ra[0]) - 1.0);
+    r.pos.y = (R)(2.0 * u01(ra[1]) - 1.0);
+    r.pos.z = (R)(2.0 * u01(ra[2]) - 1.0);
     const double r1 = sqrt(-2.0 * log(u01(ra[3])));
     const double r2 = sqrt(-2.0 * log(u01(rb[0])));
     const double t1 = 6.283185307179586 * u01(rb[1]);
     const double t2 = 6.283185307179586 * u01(rb[2]);
-    p.ux[n] = (R)(a.vth[0] * r1 * cos(t1));
-    p.uy[n] = (R)(a.vth[1] * r1 * sin(t1));
-    p.uz[n] = (R)(a.vth[2] * r2 * cos(t2));
-    p.w[n] = (R)a.weight;
+    r.mom.x = (R)(a.vth[0] * r1 * cos(t1));
+    r.mom.y = (R)(a.vth[1] * r1 * sin(t1));
+    r.mom.z = (R)(a.vth[2] * r2 * cos(t2));
+    r.mom.w = (R)a.weight;
     const long long c = (long long)(k / (unsigned long long)a.nppc);
     const int ix = (int)(c % a.gnx);
     const int iy = (int)((c / a.gnx) % a.gny);
     const int iz = (int)(c / ((long long)a.gnx * a.gny));
-    p.cell[n] = (ix + 1) + (a.lnx + 2) * ((iy + 1) + (a.lny + 2) * (iz - a.z0 + 1));
+    r.pos.w = cell_to_real((ix + 1) + (a.lnx + 2) * ((iy + 1) + (a.lny + 2) * (iz - a.z0 + 1)), R(0));
+    p.rec[n] = r;
 }
 
 }  // namespace cpic

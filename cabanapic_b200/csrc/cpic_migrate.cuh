@@ -5,7 +5,9 @@
 // slab's low/high z face in the ghost plane z = 0 / z = nz+1 (what the reference does for any
 // non-periodic boundary, src/move_p.h:257-352).  These kernels pull such particles out of the
 // store into two struct-of-arrays send buffers (cell index already re-based to the receiving
-// slab's numbering) and close the holes they leave, so the store stays dense.
+// slab's numbering) and close the holes they leave, so the store stays dense.  k_pack_records /
+// k_unpack_records convert between such member arrays and the record store; the host transfers
+// (cpic_upload_particles / cpic_download_particles) go through them chunk by chunk as well.
 //
 // Send buffer layout (both buffers, capacity `cap` particles): member m (dx dy dz ux uy uz w) at
 // byte offset m*cap*sizeof(R); cell (int32) at byte offset 7*cap*sizeof(R).
@@ -41,14 +43,15 @@ __global__ void __launch_bounds__(256) k_extract_mark(Particles<R> p, long long 
                                                       unsigned* __restrict__ counters) {
     const long long n = blockIdx.x * 256LL + threadIdx.x;
     if (n >= np) return;
-    const int c = p.cell[n];
+    const int c = p.cell(n);
     const int side = z_side(c, plane, nz);
     if (!side) return;
     const unsigned slot = atomicAdd(counters + (side - 1), 1u);
     if (slot >= cap) { counters[2] = 1u; return; }
     SendBuf<R>& b = side == 1 ? lo : hi;
-    b.m[0][slot] = p.dx[n]; b.m[1][slot] = p.dy[n]; b.m[2][slot] = p.dz[n];
-    b.m[3][slot] = p.ux[n]; b.m[4][slot] = p.uy[n]; b.m[5][slot] = p.uz[n]; b.m[6][slot] = p.w[n];
+    const PRec<R> r = p.rec[n];
+    b.m[0][slot] = r.pos.x; b.m[1][slot] = r.pos.y; b.m[2][slot] = r.pos.z;
+    b.m[3][slot] = r.mom.x; b.m[4][slot] = r.mom.y; b.m[5][slot] = r.mom.z; b.m[6][slot] = r.mom.w;
     b.cell[slot] = c + (side == 1 ? rebase_lo : rebase_hi);
 }
 
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) k_extract_lists(Particles<R> p, long long
                                                        unsigned* __restrict__ counters) {
     const long long n = blockIdx.x * 256LL + threadIdx.x;
     if (n >= np) return;
-    const bool leaving = z_side(p.cell[n], plane, nz) != 0;
+    const bool leaving = z_side(p.cell(n), plane, nz) != 0;
     if (n < np_new) {
         if (leaving) lists[atomicAdd(counters + 3, 1u)] = (unsigned)n;
     } else if (!leaving) {
@@ -74,9 +77,27 @@ __global__ void __launch_bounds__(256) k_extract_fill(Particles<R> p, const unsi
     const long long j = blockIdx.x * 256LL + threadIdx.x;
     if (j >= counters[3]) return;
     const unsigned h = lists[j], d = lists[cap + j];
-    p.dx[h] = p.dx[d]; p.dy[h] = p.dy[d]; p.dz[h] = p.dz[d];
-    p.ux[h] = p.ux[d]; p.uy[h] = p.uy[d]; p.uz[h] = p.uz[d];
-    p.w[h] = p.w[d]; p.cell[h] = p.cell[d];
+    p.rec[h] = p.rec[d];
+}
+
+// Struct-of-arrays exchange buffer (SendBuf, or a staging chunk of a host transfer) <-> records.
+template <class R>
+__global__ void __launch_bounds__(256) k_pack_records(Particles<R> p, long long first, SendBuf<R> b, long long n) {
+    const long long j = blockIdx.x * 256LL + threadIdx.x;
+    if (j >= n) return;
+    PRec<R> r;
+    r.pos.x = b.m[0][j]; r.pos.y = b.m[1][j]; r.pos.z = b.m[2][j]; r.pos.w = cell_to_real(b.cell[j], R(0));
+    r.mom.x = b.m[3][j]; r.mom.y = b.m[4][j]; r.mom.z = b.m[5][j]; r.mom.w = b.m[6][j];
+    p.rec[first + j] = r;
+}
+template <class R>
+__global__ void __launch_bounds__(256) k_unpack_records(Particles<R> p, long long first, SendBuf<R> b, long long n) {
+    const long long j = blockIdx.x * 256LL + threadIdx.x;
+    if (j >= n) return;
+    const PRec<R> r = p.rec[first + j];
+    b.m[0][j] = r.pos.x; b.m[1][j] = r.pos.y; b.m[2][j] = r.pos.z;
+    b.m[3][j] = r.mom.x; b.m[4][j] = r.mom.y; b.m[5][j] = r.mom.z; b.m[6][j] = r.mom.w;
+    b.cell[j] = real_to_cell(r.pos.w);
 }
 
 }  // namespace cpic

@@ -4,10 +4,11 @@
 // Reference: push<>, src/push.h:65-295; move_p<>, src/move_p.h:59-374 (with
 // detect_leaving_domain :9-54); uncenter_particles, src/uncenter_p.h:27-98.
 //
-// Layout: particles are struct-of-arrays (8 member arrays), one thread per particle, so a
-// warp reads/writes 32 consecutive elements of each member (fully coalesced).  The
-// interpolator record of the particle's cell is fetched with 128-bit loads through the
-// read-only path (cell-sorted particles make these warp-wide broadcasts of one record).
+// Layout: particles are 32-byte (float) / 64-byte (double) records (PRec, cpic_common.cuh), one
+// thread per particle here, so a warp reads 32 consecutive records with one 256-bit load per lane
+// (two in double) and writes the two halves it changes.  The interpolator record of the particle's
+// cell is fetched with 128-bit loads through the read-only path (cell-sorted particles make these
+// warp-wide broadcasts of one record).
 //
 // Deposit: every streak adds 12 values (jx[4] jy[4] jz[4]) to its cell's accumulator row.
 // The first streak of every particle -- the only one for the ~87 % that stay in their
@@ -19,12 +20,6 @@
 #include "cpic_common.cuh"
 
 namespace cpic {
-
-template <class R>
-struct Particles {
-    R *dx, *dy, *dz, *ux, *uy, *uz, *w;
-    int* cell;
-};
 
 template <class R>
 struct PushArgs {
@@ -345,11 +340,10 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
         const long long pn = ml.idx[m];
         (void)c_in;
         if constexpr (OUTOFPLACE) {
-            a.dst.dx[pn] = px; a.dst.dy[pn] = py; a.dst.dz[pn] = pz; a.dst.cell[pn] = c;
+            a.dst.store_pos(pn, px, py, pz, c);
             atomicAdd(a.hist + c, 1u);
         } else {
-            a.p.dx[pn] = px; a.p.dy[pn] = py; a.p.dz[pn] = pz;
-            if (c != c_in) a.p.cell[pn] = c;
+            a.p.store_pos(pn, px, py, pz, c);
             if (a.hist) atomicAdd(a.hist + c, 1u);
         }
     }
@@ -376,8 +370,9 @@ k_push(PushArgs<R> a) {
     if (tile < ntiles) {
         const long long n = tile * 32 + lane;
         if (n < a.np) {
-            ii = a.p.cell[n]; x = a.p.dx[n]; y = a.p.dy[n]; z = a.p.dz[n];
-            ux = a.p.ux[n]; uy = a.p.uy[n]; uz = a.p.uz[n]; w = a.p.w[n];
+            const PRec<R> r = a.p.rec[n];
+            ii = real_to_cell(r.pos.w); x = r.pos.x; y = r.pos.y; z = r.pos.z;
+            ux = r.mom.x; uy = r.mom.y; uz = r.mom.z; w = r.mom.w;
         }
     }
     for (; tile < ntiles; tile += stride) {
@@ -389,8 +384,9 @@ k_push(PushArgs<R> a) {
         if (PREFETCH) {
             const long long nn = (tile + stride) * 32 + lane;
             if (nn < a.np) {
-                ii_n = a.p.cell[nn]; x_n = a.p.dx[nn]; y_n = a.p.dy[nn]; z_n = a.p.dz[nn];
-                ux_n = a.p.ux[nn]; uy_n = a.p.uy[nn]; uz_n = a.p.uz[nn]; w_n = a.p.w[nn];
+                const PRec<R> r = a.p.rec[nn];
+                ii_n = real_to_cell(r.pos.w); x_n = r.pos.x; y_n = r.pos.y; z_n = r.pos.z;
+                ux_n = r.mom.x; uy_n = r.mom.y; uz_n = r.mom.z; w_n = r.mom.w;
             }
         }
 
@@ -427,7 +423,7 @@ k_push(PushArgs<R> a) {
             uy = madd<FMA>(v4, mdiff<FMA>(v2, cbx, v0, cbz), uy);
             uz = madd<FMA>(v4, mdiff<FMA>(v0, cby, v1, cbx), uz);
             ux += hax; uy += hay; uz += haz;                                  // second half kick
-            a.p.ux[n] = ux; a.p.uy[n] = uy; a.p.uz[n] = uz;                   // :165-167
+            a.p.store_mom(n, ux, uy, uz, w);                                  // :165-167
 
             v0 = one / (R)sqrtf((float)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));  // :169
             ux *= a.cdt_dx; uy *= a.cdt_dy; uz *= a.cdt_dz;                   // this order, :171-176
@@ -438,7 +434,7 @@ k_push(PushArgs<R> a) {
 
             if (v3 <= one && v4 <= one && v5n <= one && -v3 <= one && -v4 <= one && -v5n <= one) {  // :187
                 stay = true;
-                a.p.dx[n] = v3; a.p.dy[n] = v4; a.p.dz[n] = v5n;
+                a.p.store_pos(n, v3, v4, v5n, ii);
                 const R v5 = q * ux * uy * uz * one_third;                    // :203
                 streak_currents<FMA>(q, ux, uy, uz, v0, v1, v2, v5, cur);
             } else {
@@ -473,8 +469,9 @@ k_push(PushArgs<R> a) {
         } else {
             const long long nn = (tile + stride) * 32 + lane;
             if (nn < a.np) {
-                ii = a.p.cell[nn]; x = a.p.dx[nn]; y = a.p.dy[nn]; z = a.p.dz[nn];
-                ux = a.p.ux[nn]; uy = a.p.uy[nn]; uz = a.p.uz[nn]; w = a.p.w[nn];
+                const PRec<R> r = a.p.rec[nn];
+                ii = real_to_cell(r.pos.w); x = r.pos.x; y = r.pos.y; z = r.pos.z;
+                ux = r.mom.x; uy = r.mom.y; uz = r.mom.z; w = r.mom.w;
             }
         }
     }
@@ -506,15 +503,16 @@ __global__ void __launch_bounds__(256) k_uncenter(Particles<R> p, long long np, 
     const R one = R(1.), one_third = R(1. / 3.), two_fifteenths = R(2. / 15.);
     const R qdt_4mc = (R)(-0.5 * (double)qdt_2mc);
     R f[IpStride<R>::value];
-    load_record(ip, p.cell[n], f);
-    const R x = p.dx[n], y = p.dy[n], z = p.dz[n];
+    const PRec<R> r = p.rec[n];
+    load_record(ip, real_to_cell(r.pos.w), f);
+    const R x = r.pos.x, y = r.pos.y, z = r.pos.z;
     const R hax = qdt_2mc * madd<FMA>(z, madd<FMA>(y, f[I_D2EXDYDZ], f[I_DEXDZ]), madd<FMA>(y, f[I_DEXDY], f[I_EX]));
     const R hay = qdt_2mc * madd<FMA>(x, madd<FMA>(z, f[I_D2EYDZDX], f[I_DEYDX]), madd<FMA>(z, f[I_DEYDZ], f[I_EY]));
     const R haz = qdt_2mc * madd<FMA>(y, madd<FMA>(x, f[I_D2EZDXDY], f[I_DEZDY]), madd<FMA>(x, f[I_DEZDX], f[I_EZ]));
     const R cbx = madd<FMA>(x, f[I_DCBXDX], f[I_CBX]);
     const R cby = madd<FMA>(y, f[I_DCBYDY], f[I_CBY]);
     const R cbz = madd<FMA>(z, f[I_DCBZDZ], f[I_CBZ]);
-    R ux = p.ux[n], uy = p.uy[n], uz = p.uz[n];
+    R ux = r.mom.x, uy = r.mom.y, uz = r.mom.z;
     R v0 = qdt_4mc / (R)sqrt((double)(one + madd<FMA>(ux, ux, madd<FMA>(uy, uy, uz * uz))));
     R v1 = madd<FMA>(cbx, cbx, madd<FMA>(cby, cby, cbz * cbz));
     R v2 = (v0 * v0) * v1;
@@ -528,7 +526,7 @@ __global__ void __launch_bounds__(256) k_uncenter(Particles<R> p, long long np, 
     uy = madd<FMA>(v4, mdiff<FMA>(v2, cbx, v0, cbz), uy);
     uz = madd<FMA>(v4, mdiff<FMA>(v0, cby, v1, cbx), uz);
     ux += hax; uy += hay; uz += haz;
-    p.ux[n] = ux; p.uy[n] = uy; p.uz[n] = uz;
+    p.store_mom(n, ux, uy, uz, r.mom.w);
 }
 
 }  // namespace cpic

@@ -1,6 +1,6 @@
 // Counting sort of the particle store by cell index -- the step the reference left
 // commented out (Cabana::sortByKey by Cell_Index, example/example.cpp:224-228).
-// Three phases: histogram of cells, exclusive scan over cells, scatter of all 8 members
+// Three phases: histogram of cells, exclusive scan over cells, scatter of the particle records
 // into the second particle buffer.  Cell-sorted order is what makes the push kernel's
 // interpolator loads warp broadcasts and its deposit a single warp-aggregated row update.
 #pragma once
@@ -27,22 +27,24 @@ __device__ __forceinline__ int run_length_at_head(int key, int lane, int& rank_i
     return head ? (next - lane) : 0;
 }
 
-__global__ void __launch_bounds__(256) k_cell_histogram(const int* __restrict__ cell, long long np, long long nc,
+template <class R>
+__global__ void __launch_bounds__(256) k_cell_histogram(Particles<R> p, long long np, long long nc,
                                                         unsigned* __restrict__ count, unsigned* __restrict__ bad) {
     const long long n = blockIdx.x * 256LL + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int c = (n < np) ? cell[n] : -1 - lane;
+    int c = (n < np) ? p.cell(n) : -1 - lane;
     if (n < np && (c < 0 || c >= nc)) { atomicAdd(bad, 1u); c = -1 - lane; }
     int rank, head_lane;
     const int len = run_length_at_head(c, lane, rank, head_lane);
     if (len > 0 && c >= 0) atomicAdd(count + c, (unsigned)len);
 }
 
-__global__ void __launch_bounds__(256) k_check_cells(const int* __restrict__ cell, long long np, long long nc,
+template <class R>
+__global__ void __launch_bounds__(256) k_check_cells(Particles<R> p, long long np, long long nc,
                                                      unsigned* __restrict__ bad) {
     const long long n = blockIdx.x * 256LL + threadIdx.x;
     if (n >= np) return;
-    const int c = cell[n];
+    const int c = p.cell(n);
     if (c < 0 || c >= nc) atomicAdd(bad, 1u);
 }
 
@@ -89,52 +91,26 @@ __global__ void __launch_bounds__(256) k_scan_add(unsigned* __restrict__ out, lo
         if (base + k < n) out[base + k] += add;
 }
 
-// Scatter: slot = cursor[cell]++ (cursor starts at the scanned offsets).  Each run of equal
-// cells inside a warp claims a contiguous block with one atomic, keeping its relative order.
+// Scatter: slot = cursor[cell]++ (cursor starts at the scanned offsets).  Each run of equal cells
+// inside a warp claims a contiguous block with one atomic, keeping its relative order.  A record is one
+// 256-bit load and one 256-bit store (float): the whole payload is in registers before the atomic's
+// round trip is needed, and every particle lands as one full 32-byte sector wherever it goes.
 template <class R>
 __global__ void __launch_bounds__(256) k_sort_scatter(Particles<R> src, Particles<R> dst, long long np,
                                                       unsigned* __restrict__ cursor) {
     const long long n = blockIdx.x * 256LL + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = n < np;
-    const int c = valid ? src.cell[n] : -1 - lane;
-    int rank, head_lane;
-    const int len = run_length_at_head(c, lane, rank, head_lane);
-    unsigned base = 0;
-    if (len > 0 && valid) base = atomicAdd(cursor + c, (unsigned)len);
-    base = __shfl_sync(0xffffffffu, base, head_lane);
-    if (!valid) return;
-    const long long d = (long long)base + rank;
-    dst.dx[d] = src.dx[n]; dst.dy[d] = src.dy[n]; dst.dz[d] = src.dz[n];
-    dst.ux[d] = src.ux[n]; dst.uy[d] = src.uy[n]; dst.uz[d] = src.uz[n];
-    dst.w[d] = src.w[n]; dst.cell[d] = c;
-}
-
-// Second-generation scatter.  The first one is latency-bound (DRAM at 37 %, profiles/r01_sort_128cube_ncu.md):
-// per warp one dependent chain  cell load -> cursor atomic -> payload loads -> stores.  Here the eight
-// member loads are issued up front into registers, so the atomic's round trip overlaps them and only
-// the stores wait for it.
-template <class R>
-__global__ void __launch_bounds__(256) k_sort_scatter2(Particles<R> src, Particles<R> dst, long long np,
-                                                       unsigned* __restrict__ cursor) {
-    const long long n = blockIdx.x * 256LL + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool valid = n < np;
     int c = -1 - lane;
-    R v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0, v6 = 0;
-    if (valid) {
-        c = src.cell[n];
-        v0 = src.dx[n]; v1 = src.dy[n]; v2 = src.dz[n]; v3 = src.ux[n]; v4 = src.uy[n]; v5 = src.uz[n]; v6 = src.w[n];
-    }
+    PRec<R> r;
+    if (valid) { r = src.rec[n]; c = real_to_cell(r.pos.w); }
     int rank, head_lane;
     const int len = run_length_at_head(c, lane, rank, head_lane);
     unsigned base = 0;
     if (len > 0 && valid) base = atomicAdd(cursor + c, (unsigned)len);
     base = __shfl_sync(0xffffffffu, base, head_lane);
     if (!valid) return;
-    const long long d = (long long)base + rank;
-    dst.dx[d] = v0; dst.dy[d] = v1; dst.dz[d] = v2; dst.ux[d] = v3; dst.uy[d] = v4; dst.uz[d] = v5; dst.w[d] = v6;
-    dst.cell[d] = c;
+    dst.rec[(long long)base + rank] = r;
 }
 
 }  // namespace cpic

@@ -27,7 +27,10 @@ def main():
             c.sort_particles()
             c.step(k, 1, 0, False)          # one step of drift
             c.load_interpolator_array(); c.clear_accumulator_array(); c.push(k); c.sync()
-            print(f"in-place push, one step after a sort: {c.last_ms(0):8.3f} ms  {56 * n / c.last_ms(0) / 1e6:8.1f} GB/s", flush=True)
+            print(f"in-place push, one step after a sort: {c.last_ms(0):8.3f} ms  {56 * n / c.last_ms(0) / 1e6:8.1f} GB/s   (that sort: {c.last_ms(1):8.3f} ms)", flush=True)
+        c.sort_particles()
+        c.load_interpolator_array(); c.clear_accumulator_array(); c.push(k); c.sync()
+        print(f"in-place push, freshly sorted: {c.last_ms(0):8.3f} ms  {56 * n / c.last_ms(0) / 1e6:8.1f} GB/s", flush=True)
     if mode in ("both", "reorder"):
         for s in range(steps):
             c.step(k, 1, cp.SORT_FUSED, False); c.sync()
