@@ -198,8 +198,9 @@ def run_ours(args):
     d = decks.uniform_plasma(nx, ny, nz, nppc)
     k, _, we = d.consts()
     n_total = d.num_particles
-    # measured at C5 (profiles/r01_bench_n1_sort_interval_*.log): 2 -> 43.2, 4 -> 38.0, 6 -> 36.9, 8 -> 35.8 ms/step
-    sort_interval = args.sort_interval if args.sort_interval is not None else 8
+    # -1 = CPIC_SORT_FUSED: the push keeps the store in cell order itself (cpic_push_reorder), no sort pass.
+    # Measured at C5 with the record store (profiles/r02_bench_n1_records_*.log): fused 34.0, sort every 8 steps 34.8 ms/step
+    sort_interval = args.sort_interval if args.sort_interval is not None else -1
     fp = cp.FP_CONTRACT if args.fp == "contract" else cp.FP_STRICT
 
     if world > 1:

@@ -324,7 +324,7 @@ struct Ctx final : CtxBase {
             mig_cap = 2 * cap_send;
         }
         *n_lo = *n_hi = 0;
-        hist_valid = false; cursor_valid = false;
+        cursor_valid = false;
         if (np == 0) return CPIC_OK;
         cudaMemsetAsync(mig_counters, 0, 8 * sizeof(unsigned), stream);
         const int plane = g.gx * g.gy;
@@ -345,17 +345,27 @@ struct Ctx final : CtxBase {
         k_extract_fill<R><<<blocks_for(n_out), 256, 0, stream>>>(P[cur], mig_lists, mig_cap, mig_counters);
         if ((rc = check_launch("k_extract_fill"))) return rc;
         np = np_new;
+        // the cell histogram of the last push stays usable: everything that sat in the two ghost planes is gone
+        // (the hole filling only permutes the rest)
+        if (hist_valid) {
+            cudaMemsetAsync(cell_count, 0, (size_t)plane * sizeof(unsigned), stream);
+            cudaMemsetAsync(cell_count + (size_t)(g.nz + 1) * plane, 0, (size_t)plane * sizeof(unsigned), stream);
+        }
         return CPIC_OK;
     }
     int append_device(const void* buf, long long cap_buf, long long n) override {
         if (n < 0 || n > cap_buf) return fail(CPIC_E_INVALID, "append_particles_device: bad count");
         if (np + n > cap) return fail(CPIC_E_CAPACITY, "append_particles_device: %lld + %lld particles exceed capacity %lld", np, n, cap);
         if (n == 0) return CPIC_OK;
-        hist_valid = false; cursor_valid = false;
+        cursor_valid = false;
         SendBuf<R> b = carve_sendbuf<R>(const_cast<void*>(buf), cap_buf);
         k_pack_records<R><<<blocks_for(n), 256, 0, stream>>>(P[cur], np, b, n);
         int rc;
         if ((rc = check_launch("k_pack_records"))) return rc;
+        if (hist_valid) {       // keep the histogram of the last push current: count the arrivals
+            k_hist_add<<<blocks_for(n), 256, 0, stream>>>(b.cell, n, g.nc, cell_count);
+            if ((rc = check_launch("k_hist_add"))) return rc;
+        }
         np += n;
         return CPIC_OK;
     }

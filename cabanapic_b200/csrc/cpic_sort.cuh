@@ -48,6 +48,15 @@ __global__ void __launch_bounds__(256) k_check_cells(Particles<R> p, long long n
     if (c < 0 || c >= nc) atomicAdd(bad, 1u);
 }
 
+// count[cell[j]] += 1 for a short list of cells (particles appended after a migration)
+__global__ void __launch_bounds__(256) k_hist_add(const int* __restrict__ cell, long long n, long long nc,
+                                                  unsigned* __restrict__ count) {
+    const long long j = blockIdx.x * 256LL + threadIdx.x;
+    if (j >= n) return;
+    const int c = cell[j];
+    if (c >= 0 && c < nc) atomicAdd(count + c, 1u);
+}
+
 // Block-wise exclusive scan of 2048 elements per block (256 threads x 8); block totals go to
 // bsum for the next level.
 constexpr int SCAN_ITEMS = 8;

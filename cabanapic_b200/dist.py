@@ -109,6 +109,10 @@ class GpuEngine:
     def push(self, k):
         self.ctx.push(k)
 
+    def push_reorder(self, k):
+        """push + cell ordering of the store in one pass (cpic_push_reorder)"""
+        self.ctx.push_reorder(k)
+
     def unload_accumulator(self, k): self.ctx.unload_accumulator_array(k)
     def fold_phase(self, phase): self.ctx.update_ghosts(3 + phase)
     def ghost_copy_local(self, which): self.ctx.update_ghosts(1 if which == "J" else 2)
@@ -280,13 +284,16 @@ class SlabStepper:
         e.advance_e_stencil(k.px, k.py, k.pz, k.dt_eps0)  # :646-664
 
     # -- one step -----------------------------------------------------------------------
-    def step(self, sort=False):
+    def step(self, sort=False, fused=False):
         e, k = self.e, self.k
         if sort:
             e.sort()
         e.load_interpolator()
         e.clear_accumulator()
-        e.push(k)
+        if fused:
+            e.push_reorder(k)
+        else:
+            e.push(k)
         self._exchange_accumulators()
         self._migrate()
         e.unload_accumulator(k)
@@ -313,13 +320,16 @@ class ReplicatedStepper:
         R = engine.real.type
         self.half = (float(R(0.5) * R(k.px)), float(R(0.5) * R(k.py)), float(R(0.5) * R(k.pz)))
 
-    def step(self, sort=False):
+    def step(self, sort=False, fused=False):
         e, k = self.e, self.k
         if sort:
             e.sort()
         e.load_interpolator()
         e.clear_accumulator()
-        e.push(k)
+        if fused:
+            e.push_reorder(k)
+        else:
+            e.push(k)
         if self.world > 1:
             dist.all_reduce(e.acc_planes())            # contribute(), example/example.cpp:248
         e.unload_accumulator(k)
@@ -345,7 +355,7 @@ class _BenchRunner:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for s in range(n):
-            self.stepper.step(sort=sort_interval > 0 and s % sort_interval == 0)
+            self.stepper.step(sort=sort_interval > 0 and s % sort_interval == 0, fused=sort_interval < 0)
         ev1.record()
         torch.cuda.synchronize()
         self.t_ms = ev0.elapsed_time(ev1)
@@ -397,7 +407,7 @@ class _BenchRunner:
         for s in range(steps):
             c._ck(L.cpic_upload_particles(c.h, *up, n))
             c._ck(L.cpic_upload_fields(c.h, fptr))
-            self.stepper.step(sort=sort_interval > 0)
+            self.stepper.step(sort=sort_interval > 0, fused=sort_interval < 0)
             c._ck(L.cpic_download_particles(c.h, *dn, cap2, C.byref(got)))
             c._ck(L.cpic_download_fields(c.h, fptr))
         if self.world > 1:

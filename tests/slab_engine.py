@@ -40,6 +40,7 @@ class OracleEngine:
     def load_interpolator(self): self.O.load_interpolator(self.s)
     def clear_accumulator(self): self.O.clear_accumulator(self.s)
     def push(self, k): self.O.push(self.s, self._ok(k), periodic=self.per)
+    def push_reorder(self, k): self.push(k)      # the order of the store is not part of the oracle's state
     def unload_accumulator(self, k): self.O.unload_accumulator(self.s, self._ok(k))
     def fold_phase(self, phase): self.O.ghost_fold_phase(self.s, phase, self.per)
     def ghost_copy_local(self, which): self.O.ghost_copy_axes(self.s, (6, 7, 8) if which == "J" else (3, 4, 5), self.per)

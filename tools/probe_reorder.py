@@ -22,6 +22,8 @@ def main():
     c = cp.Context(nx, ny, nz, 1, max_particles=n, real=np.float32)
     c.init_uniform_plasma(0, n, nx, ny, nz, nppc, weight=we)
     c.upload_fields(d.initial_fields())
+    if os.environ.get("CPIC_FP", "strict") == "contract":
+        c.set_modes(cp.FP_CONTRACT, 3)
     if mode in ("both", "inplace"):
         for s in range(steps):
             c.sort_particles()
