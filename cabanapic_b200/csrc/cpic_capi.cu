@@ -42,6 +42,9 @@ struct CtxBase {
     bool want_hist = false;    // set by cpic_step before a push that is followed by a sort
     bool hist_valid = false;   // cell_count holds the histogram of the current cells (from the last push)
     bool cursor_valid = false; // cell_count holds the exclusive scan of that histogram (ready for a reordering push)
+    bool leavers_valid = false; // slab mode: the last push listed the particles it left in the z ghost planes
+    bool ghost_clean = false;   // no particle sits in a z ghost plane (true after init_uniform_plasma or an extraction;
+                                // unknown after an upload): only then does the mover's list find every leaver
     // opt-in per-phase profile of cpic_step: 5 events per step (start, after sort, before push,
     // after push, end) on the context's stream
     bool prof_on = false;
@@ -129,7 +132,7 @@ struct Ctx final : CtxBase {
             cudaSetDevice(prm.device);
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer); cudaFree(fields); cudaFree(interp); cudaFree(acc);
-            cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists);
+            cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count);
             if (own_stream && stream) cudaStreamDestroy(stream);
         }
     }
@@ -208,7 +211,7 @@ struct Ctx final : CtxBase {
             if ((rc = check_launch("k_pack_records"))) return rc;
         }
         np = n;
-        hist_valid = false; cursor_valid = false;
+        hist_valid = false; cursor_valid = false; leavers_valid = false; ghost_clean = false;
         // bounds-check the cell indices once on upload (would have caught decks/2stream-short.cxx)
         if (n > 0) {
             k_check_cells<R><<<blocks_for(n), 256, 0, stream>>>(P[cur], n, g.nc, bad);
@@ -311,6 +314,26 @@ struct Ctx final : CtxBase {
         return check_launch("k_ghost_fold");
     }
     // ------------------------------------------------------------------ slab migration
+    unsigned* leave_list = nullptr;     // store indices of the particles the last push left in a z ghost plane
+    unsigned* leave_count = nullptr;
+    long long leave_cap = 0;
+    // (re)arm the leaver list for a push in slab mode; no-op while z is periodic inside this context
+    int arm_leave_list(PushArgs<R>& a) {
+        a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0;
+        leavers_valid = false;
+        if ((g.per & 4) || prm.boundary != CPIC_BOUNDARY_PERIODIC || !ghost_clean) return CPIC_OK;
+        int rc;
+        if (!leave_list) {
+            leave_cap = cap / 4 + 65536;
+            if ((rc = cuda(cudaMalloc(&leave_list, (size_t)leave_cap * sizeof(unsigned)), "cudaMalloc(leaver list)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&leave_count, sizeof(unsigned)), "cudaMalloc"))) return rc;
+        }
+        cudaMemsetAsync(leave_count, 0, sizeof(unsigned), stream);
+        a.leave_list = leave_list; a.leave_count = leave_count; a.leave_cap = (unsigned)leave_cap;
+        a.leave_lo = g.gx * g.gy; a.leave_hi = (g.nz + 1) * g.gx * g.gy;
+        leavers_valid = true;
+        return CPIC_OK;
+    }
     unsigned* mig_counters = nullptr;   // 8 counters
     unsigned* mig_lists = nullptr;      // 2 * mig_cap indices: [0,mig_cap) holes, [mig_cap,2*mig_cap) donors
     long long mig_cap = 0;
@@ -328,20 +351,41 @@ struct Ctx final : CtxBase {
         if (np == 0) return CPIC_OK;
         cudaMemsetAsync(mig_counters, 0, 8 * sizeof(unsigned), stream);
         const int plane = g.gx * g.gy;
-        k_extract_mark<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, plane, g.nz, carve_sendbuf<R>(lo, cap_send),
-                                                             carve_sendbuf<R>(hi, cap_send), cap_send, rebase_lo, rebase_hi, mig_counters);
+        // the last push listed the particles it left in the ghost planes: O(leavers) instead of two passes
+        // over the store (unless the list overflowed)
+        long long nl = -1;
+        if (leavers_valid) {
+            unsigned hl = 0;
+            if ((rc = cuda(cudaMemcpyAsync(&hl, leave_count, sizeof hl, cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
+            if ((rc = cuda(cudaStreamSynchronize(stream), "extract_z_leavers"))) return rc;
+            if ((long long)hl <= leave_cap) nl = hl;
+        }
+        if (nl == 0) { ghost_clean = true; return CPIC_OK; }
+        if (nl > 0)
+            k_extract_mark_list<R><<<blocks_for(nl), 256, 0, stream>>>(P[cur], leave_list, nl, plane, g.nz, carve_sendbuf<R>(lo, cap_send),
+                                                                      carve_sendbuf<R>(hi, cap_send), cap_send, rebase_lo, rebase_hi, mig_counters);
+        else
+            k_extract_mark<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, plane, g.nz, carve_sendbuf<R>(lo, cap_send),
+                                                                 carve_sendbuf<R>(hi, cap_send), cap_send, rebase_lo, rebase_hi, mig_counters);
         if ((rc = check_launch("k_extract_mark"))) return rc;
-        unsigned h[3];
+        unsigned h[6];
         if ((rc = cuda(cudaMemcpyAsync(h, mig_counters, sizeof h, cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
         if ((rc = cuda(cudaStreamSynchronize(stream), "extract_z_leavers"))) return rc;
         if (h[2] || h[0] > cap_send || h[1] > cap_send)
             return fail(CPIC_E_CAPACITY, "extract_z_leavers: %u/%u leavers exceed the send-buffer capacity %lld", h[0], h[1], cap_send);
+        if (nl > 0 && (h[5] || (long long)h[0] + h[1] != nl))
+            return fail(CPIC_E_CUDA, "extract_z_leavers: the leaver list of the last push is inconsistent (%lld listed, %u + %u found)", nl, h[0], h[1]);
         *n_lo = h[0]; *n_hi = h[1];
         const long long n_out = (long long)h[0] + h[1];
+        ghost_clean = true;
         if (n_out == 0) return CPIC_OK;
         const long long np_new = np - n_out;
-        k_extract_lists<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, np_new, plane, g.nz, mig_lists, mig_cap, mig_counters);
+        if (nl > 0)
+            k_extract_lists_list<R><<<blocks_for(nl + n_out), 256, 0, stream>>>(P[cur], leave_list, nl, np, np_new, plane, g.nz, mig_lists, mig_cap, mig_counters);
+        else
+            k_extract_lists<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, np_new, plane, g.nz, mig_lists, mig_cap, mig_counters);
         if ((rc = check_launch("k_extract_lists"))) return rc;
+        leavers_valid = false;
         k_extract_fill<R><<<blocks_for(n_out), 256, 0, stream>>>(P[cur], mig_lists, mig_cap, mig_counters);
         if ((rc = check_launch("k_extract_fill"))) return rc;
         np = np_new;
@@ -508,6 +552,7 @@ struct Ctx final : CtxBase {
         if ((rc = prepare_reorder())) return rc;
         if constexpr (std::is_same<R, float>::value) {
             PushArgs<float> a = push_args(k);
+            if ((rc = arm_leave_list(a))) return rc;
             a.dst = P[cur ^ 1];
             a.cursor = cell_count;
             a.hist = cell_count2;
@@ -541,6 +586,7 @@ struct Ctx final : CtxBase {
         a.stats = stats;
         a.hist = nullptr;
         a.dst = P[cur]; a.cursor = nullptr;
+        a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         return a;
     }
@@ -556,6 +602,7 @@ struct Ctx final : CtxBase {
         a.stats = stats;
         a.hist = nullptr;
         hist_valid = false; cursor_valid = false;
+        { int rc0 = arm_leave_list(a); if (rc0) return rc0; }
         const int dep_mode = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
         const bool p2 = std::is_same<R, float>::value && use_push2 && dep_mode == CPIC_DEPOSIT_WARP;
         if (want_hist && prm.enable_sort && p2) {      // the next step sorts: let k_push2 count the new cells
@@ -627,7 +674,7 @@ struct Ctx final : CtxBase {
             k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
             if ((rc = check_launch("k_cell_histogram"))) return rc;
         }
-        hist_valid = false; cursor_valid = false;
+        hist_valid = false; cursor_valid = false; leavers_valid = false;
         if ((rc = scan_cells())) return rc;
         k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
         if ((rc = check_launch("k_sort_scatter"))) return rc;
@@ -641,7 +688,7 @@ struct Ctx final : CtxBase {
         if (a.count < 0 || a.count > cap) return fail(CPIC_E_CAPACITY, "init_uniform_plasma: %lld particles exceed capacity %lld", a.count, cap);
         if (a.gnx != g.nx || a.gny != g.ny) return fail(CPIC_E_INVALID, "init_uniform_plasma: x/y extents must equal the context's");
         np = a.count;
-        hist_valid = false; cursor_valid = false;
+        hist_valid = false; cursor_valid = false; leavers_valid = false; ghost_clean = true;
         if (np == 0) return CPIC_OK;
         k_init_uniform_plasma<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], a);
         return check_launch("k_init_uniform_plasma");
@@ -886,7 +933,7 @@ int cpic_set_num_particles(cpic_ctx* ctx, int64_t n) {
     CTX_OR_FAIL(ctx);
     if (n < 0 || n > c->prm.max_particles) return c->fail(CPIC_E_CAPACITY, "set_num_particles: %lld out of range", (long long)n);
     c->np = n;
-    c->hist_valid = false; c->cursor_valid = false;
+    c->hist_valid = false; c->cursor_valid = false; c->leavers_valid = false; c->ghost_clean = false;
     return CPIC_OK;
 }
 

@@ -80,6 +80,43 @@ __global__ void __launch_bounds__(256) k_extract_fill(Particles<R> p, const unsi
     p.rec[h] = p.rec[d];
 }
 
+// List-driven variants: the push left the store indices of the ghost-plane particles in `list` (PushArgs::
+// leave_list), so the extraction costs O(leavers) instead of two passes over the store.
+template <class R>
+__global__ void __launch_bounds__(256) k_extract_mark_list(Particles<R> p, const unsigned* __restrict__ list, long long nl,
+                                                           int plane, int nz, SendBuf<R> lo, SendBuf<R> hi, long long cap,
+                                                           int rebase_lo, int rebase_hi, unsigned* __restrict__ counters) {
+    const long long j = blockIdx.x * 256LL + threadIdx.x;
+    if (j >= nl) return;
+    const long long n = list[j];
+    const PRec<R> r = p.rec[n];
+    const int c = real_to_cell(r.pos.w);
+    const int side = z_side(c, plane, nz);
+    if (!side) { counters[5] = 1u; return; }        // cannot happen: the list holds ghost-plane particles only
+    const unsigned slot = atomicAdd(counters + (side - 1), 1u);
+    if (slot >= cap) { counters[2] = 1u; return; }
+    SendBuf<R>& b = side == 1 ? lo : hi;
+    b.m[0][slot] = r.pos.x; b.m[1][slot] = r.pos.y; b.m[2][slot] = r.pos.z;
+    b.m[3][slot] = r.mom.x; b.m[4][slot] = r.mom.y; b.m[5][slot] = r.mom.z; b.m[6][slot] = r.mom.w;
+    b.cell[slot] = c + (side == 1 ? rebase_lo : rebase_hi);
+}
+// threads [0, nl): listed particles below np_new are holes; threads [nl, nl + (np - np_new)): the staying
+// particles of the tail [np_new, np) are the donors
+template <class R>
+__global__ void __launch_bounds__(256) k_extract_lists_list(Particles<R> p, const unsigned* __restrict__ list, long long nl,
+                                                            long long np, long long np_new, int plane, int nz,
+                                                            unsigned* __restrict__ lists, long long cap,
+                                                            unsigned* __restrict__ counters) {
+    const long long j = blockIdx.x * 256LL + threadIdx.x;
+    if (j < nl) {
+        const unsigned n = list[j];
+        if (n < np_new) lists[atomicAdd(counters + 3, 1u)] = n;
+    } else {
+        const long long n = np_new + (j - nl);
+        if (n < np && z_side(p.cell(n), plane, nz) == 0) lists[cap + atomicAdd(counters + 4, 1u)] = (unsigned)n;
+    }
+}
+
 // Struct-of-arrays exchange buffer (SendBuf, or a staging chunk of a host transfer) <-> records.
 template <class R>
 __global__ void __launch_bounds__(256) k_pack_records(Particles<R> p, long long first, SendBuf<R> b, long long n) {

@@ -39,6 +39,13 @@ struct PushArgs {
     // the segment of the cell it occupied when the step began (cursor = exclusive scan of that histogram)
     Particles<R> dst;
     unsigned* cursor;
+    // slab mode (z not periodic inside this context): the mover appends the store index of every particle
+    // it leaves in a z ghost plane (cell < leave_lo or cell >= leave_hi) to leave_list, so that the migration
+    // that follows touches only those instead of scanning the whole store
+    unsigned* leave_list;     // optional
+    unsigned* leave_count;
+    unsigned leave_cap;
+    int leave_lo, leave_hi;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -339,6 +346,10 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
         }
         const long long pn = ml.idx[m];
         (void)c_in;
+        if (a.leave_list && (c < a.leave_lo || c >= a.leave_hi)) {
+            const unsigned j = atomicAdd(a.leave_count, 1u);
+            if (j < a.leave_cap) a.leave_list[j] = (unsigned)pn;
+        }
         if constexpr (OUTOFPLACE) {
             a.dst.store_pos(pn, px, py, pz, c);
             atomicAdd(a.hist + c, 1u);

@@ -286,21 +286,47 @@ class SlabStepper:
     # -- one step -----------------------------------------------------------------------
     def step(self, sort=False, fused=False):
         e, k = self.e, self.k
+        t = self._tick
+        t(None)
         if sort:
             e.sort()
         e.load_interpolator()
         e.clear_accumulator()
+        t("sort+interp")
         if fused:
             e.push_reorder(k)
         else:
             e.push(k)
+        t("push")
         self._exchange_accumulators()
+        t("acc exchange")
         self._migrate()
+        t("migrate")
         e.unload_accumulator(k)
         self._advance_b()
         self._advance_e()
         self._advance_b()
+        t("fields+exchange")
         self.nsteps += 1
+
+    # developer phase profile (CPIC_SLAB_PROFILE=1): host wall time per phase with a device sync at every
+    # phase boundary -- it serialises the step, so the numbers explain a step, they do not time it
+    _prof = None
+
+    def _tick(self, name):
+        if self._prof is None:
+            import os
+            SlabStepper._prof = {} if os.environ.get("CPIC_SLAB_PROFILE") else False
+        if self._prof is False:
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if name is not None:
+            self._prof[name] = self._prof.get(name, 0.0) + (now - self._t_last) * 1e3
+        self._t_last = now
+
+    def profile_report(self):
+        return dict(self._prof) if self._prof else None
 
     def energies(self):
         eng, b = self.e.energies()
@@ -421,6 +447,12 @@ class _BenchRunner:
                         "exchanges, D2H local particles+fields; bytes summed over ranks"}
 
     def close(self):
+        rep = getattr(self.stepper, "profile_report", lambda: None)()
+        if rep and self.rank == 0:
+            import sys
+            n = max(getattr(self.stepper, "nsteps", 1), 1)
+            print("slab phase profile, ms/step (serialised): " + ", ".join(f"{k} {v / n:.3f}" for k, v in rep.items()),
+                  file=sys.stderr, flush=True)
         self.eng.close()
 
 
