@@ -9,9 +9,11 @@ metric    particle-steps/s of the whole time step (sort + interpolator load + pu
           BASELINE.json configs[4] / SURVEY.md §8(d): 256^3 cells x 64 particles/cell = 2^30
           particles, float, periodic, vth = 0.1 c, dt = 0.99 Courant.
 value     device-resident throughput (state already in HBM), CUDA events on the context's stream.
-e2e       the same metric through the C-ABI with HOST buffers: every e2e step uploads the whole
-          particle + field state from pinned host memory, runs one step and downloads particles,
-          fields and energies again (what a caller holding its state in host arrays pays).
+e2e       the same metric through the C-ABI with HOST buffers: every e2e step is one cpic_step_host
+          call that takes the whole particle + field state from pinned host memory and returns
+          the advanced particles, fields and energies there (what a caller holding its state in
+          host arrays pays); the particles stream through the device in chunks, H2D / push / D2H
+          overlapped, so the step is bounded by one PCIe direction.
 roofline  the push kernel: 56 algorithmic bytes per particle-step x particles per
           launch / the kernel's mean duration (CUDA events around every push launch), against
           the measured HBM copy bandwidth in MEASURED_PEAKS.json.
@@ -356,18 +358,17 @@ class SingleGpu:
         got = C.c_int64()
         c._ck(L.cpic_download_particles(c.h, *ptrs, n, C.byref(got)))
         c._ck(L.cpic_download_fields(c.h, fptr))
-        en = np.zeros((1, 2))
+        c.sync()
         t0 = time.perf_counter()
         for _ in range(steps):
-            c._ck(L.cpic_upload_particles(c.h, *ptrs, n))
-            c._ck(L.cpic_upload_fields(c.h, fptr))
-            c._ck(L.cpic_step(c.h, C.byref(self.k), 1, sort_interval, en.ctypes.data_as(C.c_void_p)))
-            c._ck(L.cpic_download_particles(c.h, *ptrs, n, C.byref(got)))
-            c._ck(L.cpic_download_fields(c.h, fptr))
+            # one call: particles stream host -> device -> host in chunks, both PCIe directions busy at once
+            en = c.step_host(self.k, host, host, hf, hf, energies=True)
         sec = time.perf_counter() - t0
         return {"value": n * steps / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": nbytes,
                 "d2h_bytes_per_step": nbytes + 16, "steps": steps, "seconds": sec,
-                "what": "per step: H2D particles+fields from pinned host, cpic_step(1), D2H particles+fields+energies"}
+                "what": "per step: ONE cpic_step_host call on pinned host arrays (8 particle members + 9 field "
+                        "components in, the same out, + energies): chunked H2D / in-place push / D2H pipeline, "
+                        "then the field advance"}
 
     def close(self):
         self.c.close()

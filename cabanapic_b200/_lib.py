@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
             "cpic_energies": [vp, C.POINTER(dbl), C.POINTER(dbl)],
             "cpic_update_ghosts": [vp, C.c_int],
             "cpic_step": [vp, C.POINTER(Consts), i64, i32, vp],
+            "cpic_step_host": [vp, C.POINTER(Consts), C.POINTER(vp), C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), vp],
             "cpic_sort_particles": [vp],
             "cpic_push_reorder": [vp, C.POINTER(Consts)],
             "cpic_init_uniform_plasma": [vp, i64, i64, i32, i32, i32, i32, i32, C.c_uint64, dbl, dbl, dbl, dbl],
@@ -144,7 +145,7 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
             "cpic_upload_accumulators", "cpic_download_accumulators", "cpic_load_interpolator_array",
             "cpic_initialize_interpolator", "cpic_clear_accumulator_array", "cpic_push", "cpic_contribute",
             "cpic_unload_accumulator_array", "cpic_advance_b", "cpic_advance_e", "cpic_uncenter_particles",
-            "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_sort_particles", "cpic_push_reorder", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
+            "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_step_host", "cpic_sort_particles", "cpic_push_reorder", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
             "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
             "cpic_set_axis_periodic", "cpic_advance_b_stencil", "cpic_advance_e_stencil", "cpic_extract_z_leavers", "cpic_append_particles_device",
             "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile"]
@@ -291,6 +292,30 @@ class Context:
     def step(self, k: Consts, nsteps=1, sort_interval=0, energies=False):
         en = np.zeros((nsteps, 2)) if energies else None
         self._ck(self.L.cpic_step(self.h, C.byref(k), nsteps, sort_interval, _p(en)))
+        return en
+
+    def step_host(self, k: Consts, p_in: dict, p_out: dict | None, f_in, f_out=None, energies=False):
+        """cpic_step_host: one step on HOST-resident state, particles streamed through the device in chunks
+        (H2D, push, D2H overlapped).  p_in / p_out: dicts of the eight member arrays (p_out may be p_in);
+        f_in / f_out: (9, nc) arrays.  Arrays are used as they are (no copies): they must be contiguous and of
+        the context's real type / int32; pinned memory makes the transfers asynchronous."""
+        n = len(p_in["cell"])
+        for d in (p_in, p_out):
+            if d is not None:
+                for kk in PARTICLE_NAMES:
+                    a = d[kk]
+                    want = np.int32 if kk == "cell" else self.real
+                    assert a.dtype == want and a.flags.c_contiguous and len(a) >= n, kk
+        pin = (C.c_void_p * 8)(*[p_in[kk].ctypes.data for kk in PARTICLE_NAMES])
+        pout = None if p_out is None else (C.c_void_p * 8)(*[p_out[kk].ctypes.data for kk in PARTICLE_NAMES])
+        assert f_in.dtype == self.real and f_in.shape == (9, self.nc) and f_in.flags.c_contiguous
+        fin = (C.c_void_p * 9)(*[f_in[m].ctypes.data for m in range(9)])
+        fout = None
+        if f_out is not None:
+            assert f_out.dtype == self.real and f_out.shape == (9, self.nc) and f_out.flags.c_contiguous
+            fout = (C.c_void_p * 9)(*[f_out[m].ctypes.data for m in range(9)])
+        en = np.zeros(2) if energies else None
+        self._ck(self.L.cpic_step_host(self.h, C.byref(k), pin, pout, n, fin, fout, _p(en)))
         return en
 
     def sort_particles(self):

@@ -95,6 +95,8 @@ struct CtxBase {
     virtual int stencil_only(int which, double px, double py, double pz, double dt_eps0) = 0;
     virtual int extract_z(void* lo, void* hi, long long cap, long long* n_lo, long long* n_hi, int rebase_lo, int rebase_hi) = 0;
     virtual int append_device(const void* buf, long long cap, long long n) = 0;
+    virtual int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
+                          const void* const fin[9], void* const fout[9], double* energies) = 0;
     virtual double* energy_scratch() = 0;
     virtual unsigned long long* stats_dev() = 0;
 };
@@ -133,6 +135,10 @@ struct Ctx final : CtxBase {
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer); cudaFree(fields); cudaFree(interp); cudaFree(acc);
             cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count);
+            for (auto b : hs_buf) cudaFree(b);
+            for (auto e : hs_ev) if (e) cudaEventDestroy(e);
+            if (hs_up) cudaStreamDestroy(hs_up);
+            if (hs_dn) cudaStreamDestroy(hs_dn);
             if (own_stream && stream) cudaStreamDestroy(stream);
         }
     }
@@ -483,7 +489,7 @@ struct Ctx final : CtxBase {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device);
         long long blocks = (long long)sms * per_sm;
-        const long long need = (np + PUSH_WARPS * 32 - 1) / (PUSH_WARPS * 32);
+        const long long need = (a.np + PUSH_WARPS * 32 - 1) / (PUSH_WARPS * 32);
         if (blocks > need) blocks = need;
         if (push_grid > 0) blocks = std::min<long long>(push_grid, need);
         kern<<<(unsigned)blocks, PUSH_WARPS * 32, 0, stream>>>(a);
@@ -513,7 +519,7 @@ struct Ctx final : CtxBase {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device);
         long long blocks = (long long)sms * per_sm;
-        const long long need = (np + PUSH2_WARPS * 64 - 1) / (PUSH2_WARPS * 64);
+        const long long need = (a.np + PUSH2_WARPS * 64 - 1) / (PUSH2_WARPS * 64);
         if (blocks > need) blocks = need;
         if (push_grid > 0) blocks = std::min<long long>(push_grid, need);
         volatile float one = 1.0f;     // a runtime value as far as the compiler is concerned (cpic_push2.cuh)
@@ -614,28 +620,129 @@ struct Ctx final : CtxBase {
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
         cudaEventRecord(ev[0], stream);
-        int dep = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
+        const int rc = launch_inplace(a);
+        cudaEventRecord(ev[1], stream);
+        ev_valid[0] = true;
+        return rc;
+    }
+    // the in-place push kernel for this context's real type, deposit mode and floating-point policy
+    int launch_inplace(const PushArgs<R>& a) {
+        const int dep = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
         const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
-        int rc;
         if constexpr (std::is_same<R, float>::value) {
             if (use_push2 && dep == CPIC_DEPOSIT_WARP) {
                 // packed sqrt/div fast path only when qdt_2mc is a well-scaled normal number (or zero)
                 const float aq = fabsf((float)a.qdt_2mc);
                 const bool fd = push2_fastds && (aq == 0.f || (aq > 1e-12f && aq < 1e12f));
-                if (want_stats) rc = fma ? launch_push2<true, true, false>(a) : launch_push2<false, true, false>(a);
-                else if (fd) rc = fma ? launch_push2<true, false, true>(a) : launch_push2<false, false, true>(a);
-                else rc = fma ? launch_push2<true, false, false>(a) : launch_push2<false, false, false>(a);
-                cudaEventRecord(ev[1], stream);
-                ev_valid[0] = true;
-                return rc;
+                if (want_stats) return fma ? launch_push2<true, true, false>(a) : launch_push2<false, true, false>(a);
+                if (fd) return fma ? launch_push2<true, false, true>(a) : launch_push2<false, false, true>(a);
+                return fma ? launch_push2<true, false, false>(a) : launch_push2<false, false, false>(a);
             }
         }
-        if (dep == CPIC_DEPOSIT_ATOMIC) rc = fma ? launch_push<true, 1>(a) : launch_push<false, 1>(a);
-        else if (dep == CPIC_DEPOSIT_ATOMIC_V4) rc = fma ? launch_push<true, 2>(a) : launch_push<false, 2>(a);
-        else rc = fma ? launch_push<true, 3>(a) : launch_push<false, 3>(a);
-        cudaEventRecord(ev[1], stream);
-        ev_valid[0] = true;
-        return rc;
+        if (dep == CPIC_DEPOSIT_ATOMIC) return fma ? launch_push<true, 1>(a) : launch_push<false, 1>(a);
+        if (dep == CPIC_DEPOSIT_ATOMIC_V4) return fma ? launch_push<true, 2>(a) : launch_push<false, 2>(a);
+        return fma ? launch_push<true, 3>(a) : launch_push<false, 3>(a);
+    }
+    // ------------------------------------------------------------------ host-resident step (cpic_step_host)
+    // Three streams: `hs_up` carries the H2D copies of chunk i+1, the context's stream packs / pushes / unpacks
+    // chunk i, `hs_dn` carries the D2H copies of chunk i-1.  Two staging chunks per direction; events order
+    // the hand-overs.  The push of a chunk is the ordinary in-place kernel on a sub-range of the store.
+    static constexpr long long HS_CHUNK = 1ll << 22;
+    cudaStream_t hs_up = nullptr, hs_dn = nullptr;
+    char* hs_buf[4] = {nullptr, nullptr, nullptr, nullptr};   // up0 up1 dn0 dn1
+    long long hs_cap = 0;
+    cudaEvent_t hs_ev[8]{};   // up_done[2] up_free[2] dn_ready[2] dn_free[2]
+    int ensure_host_stream() {
+        if (hs_up) return CPIC_OK;
+        int rc;
+        hs_cap = HS_CHUNK;
+        if (const char* e = getenv("CPIC_HOST_CHUNK")) hs_cap = std::max(64ll, atoll(e) / 64 * 64);   // developer / test knob
+        hs_cap = std::min<long long>(cap, hs_cap);
+        if ((rc = cuda(cudaStreamCreateWithFlags(&hs_up, cudaStreamNonBlocking), "cudaStreamCreate"))) return rc;
+        if ((rc = cuda(cudaStreamCreateWithFlags(&hs_dn, cudaStreamNonBlocking), "cudaStreamCreate"))) return rc;
+        for (auto& e : hs_ev)
+            if ((rc = cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate"))) return rc;
+        for (auto& b : hs_buf)
+            if ((rc = cuda(cudaMalloc(&b, (size_t)hs_cap * (7 * sizeof(R) + sizeof(int))), "cudaMalloc(host-step staging)"))) return rc;
+        return CPIC_OK;
+    }
+    int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
+                  const void* const fin[9], void* const fout[9], double* energies) override {
+        if (n < 0 || n > cap) return fail(CPIC_E_CAPACITY, "step_host: %lld particles exceed capacity %lld", n, cap);
+        int rc;
+        if ((rc = ensure_host_stream())) return rc;
+        cudaEventRecord(ev[6], stream);
+        // fields first: the interpolators every chunk's push gathers from (example/example.cpp:233-236)
+        for (int m = 0; m < F_N; ++m)
+            if ((rc = cuda(cudaMemcpyAsync(fields + (long long)m * nc_pad, fin[m], (size_t)g.nc * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D fields"))) return rc;
+        if ((rc = load_interpolator())) return rc;
+        if ((rc = clear_accumulator())) return rc;
+        cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
+        if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
+        np = n;
+        hist_valid = false; cursor_valid = false; leavers_valid = false; ghost_clean = false; want_hist = false;
+        PushArgs<R> a0 = push_args(k);
+        const int32_t* cin = static_cast<const int32_t*>(in[7]);
+        long long chunk = 0;
+        for (long long first = 0; first < n; first += hs_cap, ++chunk) {
+            const long long cn = std::min(hs_cap, n - first);
+            const int b = (int)(chunk & 1);
+            SendBuf<R> up = carve_sendbuf<R>(hs_buf[b], hs_cap), dn = carve_sendbuf<R>(hs_buf[2 + b], hs_cap);
+            // H2D of this chunk, once the pack of chunk-2 has drained the staging buffer
+            if (chunk >= 2) cudaStreamWaitEvent(hs_up, hs_ev[2 + b], 0);
+            for (int m = 0; m < 7; ++m)
+                if ((rc = cuda(cudaMemcpyAsync(up.m[m], (const R*)in[m] + first, (size_t)cn * sizeof(R), cudaMemcpyHostToDevice, hs_up), "H2D particles"))) return rc;
+            if ((rc = cuda(cudaMemcpyAsync(up.cell, cin + first, (size_t)cn * sizeof(int), cudaMemcpyHostToDevice, hs_up), "H2D cell"))) return rc;
+            cudaEventRecord(hs_ev[0 + b], hs_up);
+            // records, push (src/push.h + src/move_p.h on this chunk), members
+            cudaStreamWaitEvent(stream, hs_ev[0 + b], 0);
+            k_pack_records_checked<R><<<blocks_for(cn), 256, 0, stream>>>(P[cur], first, up, cn, g.nc, bad);
+            if ((rc = check_launch("k_pack_records_checked"))) return rc;
+            cudaEventRecord(hs_ev[2 + b], stream);
+            PushArgs<R> a = a0;
+            a.p.rec = P[cur].rec + first; a.dst = a.p; a.np = cn;
+            if ((rc = launch_inplace(a))) return rc;
+            if (out) {
+                if (chunk >= 2) cudaStreamWaitEvent(stream, hs_ev[6 + b], 0);
+                k_unpack_records<R><<<blocks_for(cn), 256, 0, stream>>>(P[cur], first, dn, cn);
+                if ((rc = check_launch("k_unpack_records"))) return rc;
+                cudaEventRecord(hs_ev[4 + b], stream);
+                cudaStreamWaitEvent(hs_dn, hs_ev[4 + b], 0);
+                for (int m = 0; m < 7; ++m)
+                    if (out[m] && (rc = cuda(cudaMemcpyAsync((R*)out[m] + first, dn.m[m], (size_t)cn * sizeof(R), cudaMemcpyDeviceToHost, hs_dn), "D2H particles"))) return rc;
+                if (out[7] && (rc = cuda(cudaMemcpyAsync((int32_t*)out[7] + first, dn.cell, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, hs_dn), "D2H cell"))) return rc;
+                cudaEventRecord(hs_ev[6 + b], hs_dn);
+            }
+        }
+        // field side of the step (example/example.cpp:248-266); the last chunks' D2H overlaps it
+        const double hx = sizeof(R) == 4 ? (double)(0.5f * (float)k.px) : 0.5 * k.px;
+        const double hy = sizeof(R) == 4 ? (double)(0.5f * (float)k.py) : 0.5 * k.py;
+        const double hz = sizeof(R) == 4 ? (double)(0.5f * (float)k.pz) : 0.5 * k.pz;
+        if ((rc = unload_accumulator(k))) return rc;
+        if ((rc = advance_b(hx, hy, hz))) return rc;
+        if ((rc = advance_e(k.px, k.py, k.pz, k.dt_eps0))) return rc;
+        if ((rc = advance_b(hx, hy, hz))) return rc;
+        double h[2] = {0, 0};
+        if (energies) {
+            if ((rc = energies_async(en_dev))) return rc;
+            if ((rc = cuda(cudaMemcpyAsync(h, en_dev, sizeof h, cudaMemcpyDeviceToHost, stream), "D2H energies"))) return rc;
+        }
+        if (fout)
+            for (int m = 0; m < F_N; ++m)
+                if (fout[m] && (rc = cuda(cudaMemcpyAsync(fout[m], fields + (long long)m * nc_pad, (size_t)g.nc * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H fields"))) return rc;
+        unsigned nbad = 0;
+        if ((rc = cuda(cudaMemcpyAsync(&nbad, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
+        cudaEventRecord(ev[7], stream);
+        ev_valid[3] = true;
+        if ((rc = cuda(cudaStreamSynchronize(stream), "step_host"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(hs_dn), "step_host (D2H)"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(hs_up), "step_host (H2D)"))) return rc;
+        if (nbad) { np = 0; return fail(CPIC_E_BAD_CELL, "step_host: %u particles have a cell index outside [0,%lld)", nbad, g.nc); }
+        if (energies) {
+            energies[0] = 0.5 * h[0];
+            energies[1] = prm.solver == CPIC_SOLVER_EM ? 0.5 * h[1] : 0.0;
+        }
+        return CPIC_OK;
     }
     int uncenter(double qdt_2mc) override {
         if (np == 0) return CPIC_OK;
@@ -900,6 +1007,15 @@ int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_
     }
     if (en) { cudaStreamSynchronize(c->stream); cudaFree(en); }
     return rc;
+}
+
+int cpic_step_host(cpic_ctx* ctx, const cpic_consts* k, const void* const in[8], void* const out[8], int64_t n,
+                   const void* const fields_in[9], void* const fields_out[9], double* energies) {
+    CTX_OR_FAIL(ctx);
+    if (!k || !in || !fields_in) return c->fail(CPIC_E_INVALID, "step_host: null argument");
+    for (int m = 0; m < 9; ++m) if (!fields_in[m]) return c->fail(CPIC_E_INVALID, "step_host: null field member %d", m);
+    if (n > 0) for (int m = 0; m < 8; ++m) if (!in[m]) return c->fail(CPIC_E_INVALID, "step_host: null particle member %d", m);
+    return c->step_host(*k, in, out, n, fields_in, fields_out, energies);
 }
 
 int cpic_push_stats_get(cpic_ctx* ctx, cpic_push_stats* out) {

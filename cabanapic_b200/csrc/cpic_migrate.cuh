@@ -127,6 +127,20 @@ __global__ void __launch_bounds__(256) k_pack_records(Particles<R> p, long long 
     r.mom.x = b.m[3][j]; r.mom.y = b.m[4][j]; r.mom.z = b.m[5][j]; r.mom.w = b.m[6][j];
     p.rec[first + j] = r;
 }
+// k_pack_records for data arriving from the host: a cell index outside [0, nc) is counted in *bad and stored
+// as cell 0 (a ghost cell), so that a push of the chunk before the host has seen the count stays in bounds.
+template <class R>
+__global__ void __launch_bounds__(256) k_pack_records_checked(Particles<R> p, long long first, SendBuf<R> b, long long n,
+                                                              long long nc, unsigned* __restrict__ bad) {
+    const long long j = blockIdx.x * 256LL + threadIdx.x;
+    if (j >= n) return;
+    int c = b.cell[j];
+    if (c < 0 || c >= nc) { atomicAdd(bad, 1u); c = 0; }
+    PRec<R> r;
+    r.pos.x = b.m[0][j]; r.pos.y = b.m[1][j]; r.pos.z = b.m[2][j]; r.pos.w = cell_to_real(c, R(0));
+    r.mom.x = b.m[3][j]; r.mom.y = b.m[4][j]; r.mom.z = b.m[5][j]; r.mom.w = b.m[6][j];
+    p.rec[first + j] = r;
+}
 template <class R>
 __global__ void __launch_bounds__(256) k_unpack_records(Particles<R> p, long long first, SendBuf<R> b, long long n) {
     const long long j = blockIdx.x * 256LL + threadIdx.x;

@@ -140,6 +140,21 @@ int  cpic_update_ghosts(cpic_ctx* ctx, int which /* 0: fold J, 1: copy J, 2: cop
 #define CPIC_SORT_FUSED (-1)   /* sort_interval: keep the store cell-ordered with cpic_push_reorder, no sort pass */
 int  cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, double* energies);
 
+/* ONE step of the same loop for a caller whose state lives in HOST memory (the reference's host build
+ * keeps everything there: example/example.cpp:58-113 allocates, :221-266 steps).  Equivalent to
+ * cpic_upload_particles + cpic_upload_fields + cpic_step(k, 1, 0, energies) + cpic_download_particles +
+ * cpic_download_fields, but the particles STREAM through the device in chunks: chunk i is pushed (in place,
+ * caller's particle order kept) while chunk i+1 is still arriving and chunk i-1 is already on its way
+ * back, so PCIe runs in both directions at once and the step costs max(H2D, D2H) instead of their sum.
+ * The eight `in` member arrays (dx dy dz ux uy uz w cell) hold n particles; the eight `out` arrays receive
+ * them after the step (out[m] may equal in[m]; out == NULL skips the download, an out[m] == NULL skips
+ * that member).  fields_in / fields_out: nine arrays of cpic_num_cells reals, as cpic_upload_fields /
+ * cpic_download_fields (fields_out may be NULL).  energies: NULL or 2 doubles (e, b after the step).
+ * Pinned host memory is what makes the copies asynchronous; pageable memory works but serialises.
+ * Afterwards the context holds the advanced state, as after the unfused sequence. */
+int  cpic_step_host(cpic_ctx* ctx, const cpic_consts* k, const void* const in[8], void* const out[8], int64_t n,
+                    const void* const fields_in[9], void* const fields_out[9], double* energies);
+
 /* Device-side Particle_Initializer for the synthetic uniform thermal plasma (the reference's
  * default initialisers also run in the execution space, src/input/deck.h:155-157): fills this
  * context's store with global particles [first, first+count) of a gnx*gny*gnz*nppc box;

@@ -233,6 +233,50 @@ def test_fused_step_equals_unfused_calls():
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("chunk", [0, 192])
+def test_step_host_streamed_equals_oracle_step(prec, chunk, monkeypatch):
+    """cpic_step_host (host-resident state, particles streamed through the device in chunks) does what the
+    reference's loop body does (example/example.cpp:221-266): particles bit-exact after each of two steps
+    (every chunk boundary incl. a ragged last chunk when chunk=192), fields and energies to accumulation-order
+    tolerance; `out` aliasing `in`, and the context left holding the advanced state."""
+    if chunk:
+        monkeypatch.setenv("CPIC_HOST_CHUNK", str(chunk))
+    R = PREC[prec]
+    s = random_state(7, 5, 4, nppc=13, prec=prec, seed=21)           # 1820 particles: 9 full chunks + 92
+    k = consts_for(7, 5, 4, prec)
+    O = Restatement(prec)
+    m = cp()
+    with m.Context(s.nx, s.ny, s.nz, 1, max_particles=s.np, real=R) as c:
+        p = {n: s.p[n].copy() for n in PARTICLE_NAMES}
+        f = s.f.copy()
+        for it in range(2):
+            en_ref = O.step(s, k, 0, 1, energies=True)[0]
+            f_out = np.empty_like(f)
+            en = c.step_host(to_k(k), p, p, f, f_out, energies=True)   # in place on the host arrays
+            for n in PARTICLE_NAMES:
+                assert np.array_equal(p[n], s.p[n]), (it, n)
+            scale = np.abs(s.f).max()
+            assert np.abs(f_out - s.f).max() <= (2e-5 if prec == "f32" else 1e-12) * scale
+            assert np.allclose(en, en_ref, rtol=1e-4 if prec == "f32" else 1e-10)
+            # feed the oracle's fields back so that the second step starts from bit-identical inputs
+            f = s.f.copy()
+        q = c.download_particles()
+        for n in PARTICLE_NAMES:
+            assert np.array_equal(q[n], s.p[n]), n
+        # no download requested: state advances on the device only
+        O.step(s, k, 0, 1)
+        c.step_host(to_k(k), p, None, f, None)
+        q = c.download_particles()
+        for n in PARTICLE_NAMES:
+            assert np.array_equal(q[n], s.p[n]), n
+        # a bad cell index is reported, not dereferenced
+        p["cell"][7] = 10 ** 6
+        with pytest.raises(m.CpicError) as e:
+            c.step_host(to_k(k), p, p, f, None)
+        assert e.value.code == -5
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_sort_particles_properties(prec):
     """Sort = a permutation, cells non-decreasing, idempotent, and physics-neutral."""
     s = random_state(7, 6, 5, nppc=30, prec=prec, seed=12)
