@@ -126,6 +126,8 @@ def lib() -> C.CDLL:
             "cpic_advance_e_stencil": [vp, dbl, dbl, dbl, dbl],
             "cpic_extract_z_leavers": [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i64), i32, i32],
             "cpic_append_particles_device": [vp, vp, i64, i64],
+            "cpic_slab_extract_async": [vp, vp, vp, i64, vp, i32, i32],
+            "cpic_slab_append_async": [vp, vp, i64, vp],
             "cpic_last_ms": [vp, C.c_int, C.POINTER(dbl)],
             "cpic_launch_count": [vp, C.POINTER(i64)],
             "cpic_enable_step_profile": [vp, i32],
@@ -147,7 +149,7 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
             "cpic_unload_accumulator_array", "cpic_advance_b", "cpic_advance_e", "cpic_uncenter_particles",
             "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_step_host", "cpic_sort_particles", "cpic_push_reorder", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
             "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
-            "cpic_set_axis_periodic", "cpic_advance_b_stencil", "cpic_advance_e_stencil", "cpic_extract_z_leavers", "cpic_append_particles_device",
+            "cpic_set_axis_periodic", "cpic_advance_b_stencil", "cpic_advance_e_stencil", "cpic_extract_z_leavers", "cpic_append_particles_device", "cpic_slab_extract_async", "cpic_slab_append_async",
             "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile"]
 
 
@@ -363,6 +365,14 @@ class Context:
         self._ck(self.L.cpic_extract_z_leavers(self.h, C.c_void_p(lo_ptr), C.c_void_p(hi_ptr), capacity, C.byref(a),
                                                C.byref(b), rebase_lo, rebase_hi))
         return a.value, b.value
+
+    def slab_extract_async(self, lo_ptr, hi_ptr, capacity, counts_dev_ptr, rebase_lo, rebase_hi):
+        """cpic_slab_extract_async: counts (int64[2], device) instead of a host round trip."""
+        self._ck(self.L.cpic_slab_extract_async(self.h, C.c_void_p(lo_ptr), C.c_void_p(hi_ptr), capacity,
+                                                C.c_void_p(counts_dev_ptr), rebase_lo, rebase_hi))
+
+    def slab_append_async(self, ptr, capacity, count_dev_ptr):
+        self._ck(self.L.cpic_slab_append_async(self.h, C.c_void_p(ptr), capacity, C.c_void_p(count_dev_ptr)))
 
     def append_particles_device(self, ptr, capacity, n):
         self._ck(self.L.cpic_append_particles_device(self.h, C.c_void_p(ptr), capacity, n))

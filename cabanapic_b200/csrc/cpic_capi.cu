@@ -95,6 +95,10 @@ struct CtxBase {
     virtual int stencil_only(int which, double px, double py, double pz, double dt_eps0) = 0;
     virtual int extract_z(void* lo, void* hi, long long cap, long long* n_lo, long long* n_hi, int rebase_lo, int rebase_hi) = 0;
     virtual int append_device(const void* buf, long long cap, long long n) = 0;
+    virtual int slab_extract_async(void* lo, void* hi, long long cap, long long* counts_dev, int rebase_lo, int rebase_hi) = 0;
+    virtual int slab_append_async(const void* buf, long long cap, const long long* count_dev) = 0;
+    virtual int sync_np() = 0;      // device-count mode -> host-count mode (synchronises); no-op otherwise
+    bool dev_count = false;         // slab mode: np lives in dc[0] on the device, the host's np is stale
     virtual int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
                           const void* const fin[9], void* const fout[9], double* energies) = 0;
     virtual double* energy_scratch() = 0;
@@ -134,7 +138,7 @@ struct Ctx final : CtxBase {
             cudaSetDevice(prm.device);
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer); cudaFree(fields); cudaFree(interp); cudaFree(acc);
-            cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count);
+            cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count); cudaFree(dc);
             for (auto b : hs_buf) cudaFree(b);
             for (auto e : hs_ev) if (e) cudaEventDestroy(e);
             if (hs_up) cudaStreamDestroy(hs_up);
@@ -419,6 +423,84 @@ struct Ctx final : CtxBase {
         np += n;
         return CPIC_OK;
     }
+    // ------------------------------------------------------------------ slab migration, counts on the device
+    long long* dc = nullptr;            // [0] np [1] error flags [2] [3] leavers of the last extraction
+    int enter_dev_count() {
+        if (dev_count) return CPIC_OK;
+        int rc;
+        if (!dc && (rc = cuda(cudaMalloc(&dc, 4 * sizeof(long long)), "cudaMalloc"))) return rc;
+        const long long h[4] = {np, 0, 0, 0};
+        if ((rc = cuda(cudaMemcpyAsync(dc, h, sizeof h, cudaMemcpyHostToDevice, stream), "H2D counts"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(stream), "enter_dev_count"))) return rc;
+        dev_count = true;
+        return CPIC_OK;
+    }
+    int sync_np() override {
+        if (!dev_count) return CPIC_OK;
+        long long h[4] = {0, 0, 0, 0};
+        int rc;
+        if ((rc = cuda(cudaMemcpyAsync(h, dc, sizeof h, cudaMemcpyDeviceToHost, stream), "D2H counts"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(stream), "sync_np"))) return rc;
+        dev_count = false;
+        np = h[0];
+        if (h[1] & 1) return fail(CPIC_E_CAPACITY, "slab_extract_async: leavers exceeded the send-buffer capacity");
+        if (h[1] & 4) return fail(CPIC_E_CAPACITY, "slab_append_async: arrivals exceeded the store capacity %lld", cap);
+        if (h[1]) return fail(CPIC_E_CUDA, "slab_extract_async: the leaver list of a push overflowed or was inconsistent");
+        return CPIC_OK;
+    }
+    int slab_extract_async(void* lo, void* hi, long long cap_send, long long* counts_dev, int rebase_lo, int rebase_hi) override {
+        int rc;
+        if (!can_reorder()) return fail(CPIC_E_UNSUPPORTED, "slab_extract_async: needs the float reordering push (enable_sort, warp deposit)");
+        if (cap_send < 1) return fail(CPIC_E_INVALID, "slab_extract_async: capacity must be positive");
+        if (!leavers_valid) {
+            // The last push did not list its leavers (first step after an upload: the ghost planes were not known
+            // to be empty): one synchronising scan-based extraction, after which every push arms its list.
+            if ((rc = sync_np())) return rc;
+            long long a = 0, b = 0;
+            if ((rc = extract_z(lo, hi, cap_send, &a, &b, rebase_lo, rebase_hi))) return rc;
+            if ((rc = enter_dev_count())) return rc;
+            const long long h[2] = {a, b};
+            if ((rc = cuda(cudaMemcpyAsync(counts_dev, h, sizeof h, cudaMemcpyHostToDevice, stream), "H2D counts"))) return rc;
+            return cuda(cudaStreamSynchronize(stream), "slab_extract_async");
+        }
+        if ((rc = enter_dev_count())) return rc;
+        if (!mig_counters && (rc = cuda(cudaMalloc(&mig_counters, 8 * sizeof(unsigned)), "cudaMalloc"))) return rc;
+        if (mig_cap < 2 * cap_send) {
+            cudaFree(mig_lists); mig_lists = nullptr;
+            if ((rc = cuda(cudaMalloc(&mig_lists, (size_t)4 * cap_send * sizeof(unsigned)), "cudaMalloc(migration lists)"))) return rc;
+            mig_cap = 2 * cap_send;
+        }
+        cursor_valid = false;
+        cudaMemsetAsync(mig_counters, 0, 8 * sizeof(unsigned), stream);
+        const int plane = g.gx * g.gy;
+        const unsigned nb = blocks_for(2 * cap_send);
+        k_extract_mark_dev<R><<<nb, 256, 0, stream>>>(P[cur], leave_list, leave_count, (unsigned)leave_cap, plane, g.nz, carve_sendbuf<R>(lo, cap_send),
+                                                    carve_sendbuf<R>(hi, cap_send), cap_send, rebase_lo, rebase_hi, mig_counters, dc);
+        if ((rc = check_launch("k_extract_mark_dev"))) return rc;
+        k_extract_lists_dev<R><<<2 * nb, 256, 0, stream>>>(P[cur], leave_list, leave_count, plane, g.nz, mig_lists, mig_cap, mig_counters, dc);
+        if ((rc = check_launch("k_extract_lists_dev"))) return rc;
+        k_extract_fill_dev<R><<<nb, 256, 0, stream>>>(P[cur], mig_lists, mig_cap, mig_counters, dc);
+        if ((rc = check_launch("k_extract_fill_dev"))) return rc;
+        k_extract_finish_dev<<<1, 1, 0, stream>>>(mig_counters, leave_count, dc, counts_dev);
+        if ((rc = check_launch("k_extract_finish_dev"))) return rc;
+        leavers_valid = false;
+        ghost_clean = true;
+        if (hist_valid) {      // everything that sat in the two ghost planes is gone (the hole filling only permutes the rest)
+            cudaMemsetAsync(cell_count, 0, (size_t)plane * sizeof(unsigned), stream);
+            cudaMemsetAsync(cell_count + (size_t)(g.nz + 1) * plane, 0, (size_t)plane * sizeof(unsigned), stream);
+        }
+        return CPIC_OK;
+    }
+    int slab_append_async(const void* buf, long long cap_buf, const long long* count_dev) override {
+        int rc;
+        if (!dev_count) return fail(CPIC_E_INVALID, "slab_append_async: call slab_extract_async first");
+        cursor_valid = false;
+        SendBuf<R> b = carve_sendbuf<R>(const_cast<void*>(buf), cap_buf);
+        k_append_dev<R><<<blocks_for(cap_buf), 256, 0, stream>>>(P[cur], b, cap_buf, count_dev, cap, g.nc, hist_valid ? cell_count : nullptr, dc);
+        if ((rc = check_launch("k_append_dev"))) return rc;
+        k_append_finish_dev<<<1, 1, 0, stream>>>(count_dev, dc);
+        return check_launch("k_append_finish_dev");
+    }
     int update_ghosts(int which) override {
         if (which == 0) return ghost_fold();
         if (which == 3) return fold_phase(0);
@@ -562,6 +644,7 @@ struct Ctx final : CtxBase {
             a.dst = P[cur ^ 1];
             a.cursor = cell_count;
             a.hist = cell_count2;
+            if (dev_count) { a.np_dev = dc; a.np = cap; }      // (a.np then only sizes the grid)
             cudaMemsetAsync(cell_count2, 0, (size_t)g.nc * sizeof(unsigned), stream);
             if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
             cudaEventRecord(ev[0], stream);
@@ -594,11 +677,17 @@ struct Ctx final : CtxBase {
         a.dst = P[cur]; a.cursor = nullptr;
         a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
+        a.np_dev = nullptr;
+        a.ko = 0;
+#ifdef PUSH2_KO_RT
+        if (const char* e = getenv("CPIC_PUSH2_KO")) a.ko = atoi(e);
+#endif
         return a;
     }
     int push(const cpic_consts& k) override {
         if (np == 0) return CPIC_OK;
         PushArgs<R> a;
+        a.ko = 0; a.np_dev = nullptr;
         a.dst = P[cur]; a.cursor = nullptr;
         a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
         a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
@@ -840,6 +929,11 @@ int validate(const cpic_params& p, std::string& why) {
     CtxBase* c = reinterpret_cast<CtxBase*>(ctx); \
     { cudaError_t e_ = cudaSetDevice(c->prm.device); if (e_ != cudaSuccess) return c->cuda(e_, "cudaSetDevice"); }
 
+// entry points that read the host's particle count: leave the device-count mode of the slab exchange first
+#define CTX_HOSTNP(ctx) \
+    CTX_OR_FAIL(ctx); \
+    { int rc_np_ = c->sync_np(); if (rc_np_) return rc_np_; }
+
 }  // namespace
 
 extern "C" {
@@ -882,18 +976,23 @@ void cpic_destroy(cpic_ctx* ctx) {
 
 int cpic_sync(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->cuda(cudaStreamSynchronize(c->stream), "sync"); }
 int cpic_num_cells(const cpic_ctx* ctx, int64_t* out) { if (!ctx || !out) return CPIC_E_INVALID; *out = reinterpret_cast<const CtxBase*>(ctx)->g.nc; return CPIC_OK; }
-int cpic_num_particles(const cpic_ctx* ctx, int64_t* out) { if (!ctx || !out) return CPIC_E_INVALID; *out = reinterpret_cast<const CtxBase*>(ctx)->np; return CPIC_OK; }
+int cpic_num_particles(const cpic_ctx* ctx, int64_t* out) {
+    if (!out) return CPIC_E_INVALID;
+    CTX_HOSTNP(const_cast<cpic_ctx*>(ctx));
+    *out = c->np;
+    return CPIC_OK;
+}
 
 int cpic_upload_particles(cpic_ctx* ctx, const void* dx, const void* dy, const void* dz, const void* ux, const void* uy,
                           const void* uz, const void* w, const int32_t* cell, int64_t n) {
-    CTX_OR_FAIL(ctx);
+    CTX_HOSTNP(ctx);
     if (n > 0 && (!dx || !dy || !dz || !ux || !uy || !uz || !w || !cell)) return c->fail(CPIC_E_INVALID, "upload_particles: null member array");
     const void* m[7] = {dx, dy, dz, ux, uy, uz, w};
     return c->upload_particles(m, cell, n);
 }
 int cpic_download_particles(cpic_ctx* ctx, void* dx, void* dy, void* dz, void* ux, void* uy, void* uz, void* w,
                             int32_t* cell, int64_t capacity, int64_t* n_out) {
-    CTX_OR_FAIL(ctx);
+    CTX_HOSTNP(ctx);
     void* m[7] = {dx, dy, dz, ux, uy, uz, w};
     long long n = 0;
     int rc = c->download_particles(m, cell, capacity, &n);
@@ -914,20 +1013,20 @@ int cpic_download_accumulators(cpic_ctx* ctx, void* acc) { CTX_OR_FAIL(ctx); if 
 int cpic_load_interpolator_array(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->load_interpolator(); }
 int cpic_initialize_interpolator(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->initialize_interpolator(); }
 int cpic_clear_accumulator_array(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->clear_accumulator(); }
-int cpic_push(cpic_ctx* ctx, const cpic_consts* k) { CTX_OR_FAIL(ctx); if (!k) return c->fail(CPIC_E_INVALID, "push: null consts"); return c->push(*k); }
+int cpic_push(cpic_ctx* ctx, const cpic_consts* k) { CTX_HOSTNP(ctx); if (!k) return c->fail(CPIC_E_INVALID, "push: null consts"); return c->push(*k); }
 int cpic_contribute(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return CPIC_OK; }
 int cpic_unload_accumulator_array(cpic_ctx* ctx, const cpic_consts* k) { CTX_OR_FAIL(ctx); if (!k) return c->fail(CPIC_E_INVALID, "unload: null consts"); return c->unload_accumulator(*k); }
 int cpic_advance_b(cpic_ctx* ctx, double px, double py, double pz) { CTX_OR_FAIL(ctx); return c->advance_b(px, py, pz); }
 int cpic_advance_e(cpic_ctx* ctx, double px, double py, double pz, double dt_eps0) { CTX_OR_FAIL(ctx); return c->advance_e(px, py, pz, dt_eps0); }
-int cpic_uncenter_particles(cpic_ctx* ctx, double qdt_2mc) { CTX_OR_FAIL(ctx); return c->uncenter(qdt_2mc); }
+int cpic_uncenter_particles(cpic_ctx* ctx, double qdt_2mc) { CTX_HOSTNP(ctx); return c->uncenter(qdt_2mc); }
 int cpic_update_ghosts(cpic_ctx* ctx, int which) { CTX_OR_FAIL(ctx); return c->update_ghosts(which); }
-int cpic_sort_particles(cpic_ctx* ctx) { CTX_OR_FAIL(ctx); return c->sort(); }
+int cpic_sort_particles(cpic_ctx* ctx) { CTX_HOSTNP(ctx); return c->sort(); }
 int cpic_push_reorder(cpic_ctx* ctx, const cpic_consts* k) { CTX_OR_FAIL(ctx); if (!k) return c->fail(CPIC_E_INVALID, "push_reorder: null consts"); return c->push_reorder(*k); }
 
 int cpic_init_uniform_plasma(cpic_ctx* ctx, int64_t first, int64_t count, int32_t gnx, int32_t gny, int32_t gnz,
                              int32_t nppc, int32_t z0, uint64_t seed, double vthx, double vthy, double vthz,
                              double weight) {
-    CTX_OR_FAIL(ctx);
+    CTX_HOSTNP(ctx);
     if (nppc < 1 || gnx < 1 || gny < 1 || gnz < 1 || first < 0) return c->fail(CPIC_E_INVALID, "init_uniform_plasma: bad arguments");
     const long long total = (long long)gnx * gny * gnz * nppc;
     if (first + count > total) return c->fail(CPIC_E_INVALID, "init_uniform_plasma: slice exceeds the global particle list");
@@ -956,7 +1055,7 @@ int cpic_energies(cpic_ctx* ctx, double* e_energy, double* b_energy) {
 }
 
 int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, double* energies) {
-    CTX_OR_FAIL(ctx);
+    CTX_HOSTNP(ctx);
     if (!k || nsteps < 0 || sort_interval < CPIC_SORT_FUSED) return c->fail(CPIC_E_INVALID, "step: bad arguments");
     int rc = CPIC_OK;
     double* en = nullptr;
@@ -1011,7 +1110,7 @@ int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_
 
 int cpic_step_host(cpic_ctx* ctx, const cpic_consts* k, const void* const in[8], void* const out[8], int64_t n,
                    const void* const fields_in[9], void* const fields_out[9], double* energies) {
-    CTX_OR_FAIL(ctx);
+    CTX_HOSTNP(ctx);
     if (!k || !in || !fields_in) return c->fail(CPIC_E_INVALID, "step_host: null argument");
     for (int m = 0; m < 9; ++m) if (!fields_in[m]) return c->fail(CPIC_E_INVALID, "step_host: null field member %d", m);
     if (n > 0) for (int m = 0; m < 8; ++m) if (!in[m]) return c->fail(CPIC_E_INVALID, "step_host: null particle member %d", m);
@@ -1046,7 +1145,7 @@ int cpic_set_stream(cpic_ctx* ctx, void* cuda_stream) {
 }
 
 int cpic_set_num_particles(cpic_ctx* ctx, int64_t n) {
-    CTX_OR_FAIL(ctx);
+    CTX_HOSTNP(ctx);
     if (n < 0 || n > c->prm.max_particles) return c->fail(CPIC_E_CAPACITY, "set_num_particles: %lld out of range", (long long)n);
     c->np = n;
     c->hist_valid = false; c->cursor_valid = false; c->leavers_valid = false; c->ghost_clean = false;
@@ -1064,7 +1163,7 @@ int cpic_set_axis_periodic(cpic_ctx* ctx, int32_t px, int32_t py, int32_t pz) {
 
 int cpic_extract_z_leavers(cpic_ctx* ctx, void* lo_buf, void* hi_buf, int64_t capacity, int64_t* n_lo, int64_t* n_hi,
                            int32_t rebase_lo, int32_t rebase_hi) {
-    CTX_OR_FAIL(ctx);
+    CTX_HOSTNP(ctx);
     if (!lo_buf || !hi_buf || !n_lo || !n_hi) return c->fail(CPIC_E_INVALID, "extract_z_leavers: null argument");
     long long a = 0, b = 0;
     int rc = c->extract_z(lo_buf, hi_buf, capacity, &a, &b, rebase_lo, rebase_hi);
@@ -1072,14 +1171,27 @@ int cpic_extract_z_leavers(cpic_ctx* ctx, void* lo_buf, void* hi_buf, int64_t ca
     return rc;
 }
 
-int cpic_append_particles_device(cpic_ctx* ctx, const void* buf, int64_t capacity, int64_t n) {
+int cpic_slab_extract_async(cpic_ctx* ctx, void* lo_buf, void* hi_buf, int64_t capacity, int64_t* counts_dev,
+                            int32_t rebase_lo, int32_t rebase_hi) {
     CTX_OR_FAIL(ctx);
+    if (!lo_buf || !hi_buf || !counts_dev) return c->fail(CPIC_E_INVALID, "slab_extract_async: null argument");
+    return c->slab_extract_async(lo_buf, hi_buf, capacity, reinterpret_cast<long long*>(counts_dev), rebase_lo, rebase_hi);
+}
+
+int cpic_slab_append_async(cpic_ctx* ctx, const void* buf, int64_t capacity, const int64_t* count_dev) {
+    CTX_OR_FAIL(ctx);
+    if (!buf || !count_dev || capacity < 1) return c->fail(CPIC_E_INVALID, "slab_append_async: bad argument");
+    return c->slab_append_async(buf, capacity, reinterpret_cast<const long long*>(count_dev));
+}
+
+int cpic_append_particles_device(cpic_ctx* ctx, const void* buf, int64_t capacity, int64_t n) {
+    CTX_HOSTNP(ctx);
     if (!buf && n > 0) return c->fail(CPIC_E_INVALID, "append_particles_device: null buffer");
     return c->append_device(buf, capacity, n);
 }
 
 int cpic_set_modes(cpic_ctx* ctx, int32_t fp_mode, int32_t deposit_mode) {
-    CTX_OR_FAIL(ctx);
+    CTX_HOSTNP(ctx);
     if ((fp_mode != CPIC_FP_STRICT && fp_mode != CPIC_FP_CONTRACT) || deposit_mode < 0 || deposit_mode > 3)
         return c->fail(CPIC_E_INVALID, "set_modes: bad mode");
     c->prm.fp_mode = fp_mode;

@@ -46,7 +46,23 @@ struct PushArgs {
     unsigned* leave_count;
     unsigned leave_cap;
     int leave_lo, leave_hi;
+    const long long* np_dev;   // optional: the particle count lives on the device (overrides np; k_push2 only)
+    int ko;   // developer knock-out mask (timing studies; honoured only by builds with -DPUSH2_KO_RT, see cpic_push2.cuh)
 };
+// Knock-outs for timing studies (results are wrong): compile-time mask PUSH2_KO, or with -DPUSH2_KO_RT the
+// run-time mask a.ko (env CPIC_PUSH2_KO) so that one knocked-out step can be timed on a steady-state store.
+//   1 no first-streak deposit   2 no record stores   4 every gather reads cell 0/1   8 no slot claims
+//   16 movers not drained       32 no straddling-pair deposit path   64 drain: no reductions
+//   128 drain: no position store / histogram atomic   256 first streak: summed but not reduced
+//   512 no histogram atomics in the main path
+#ifndef PUSH2_KO
+#define PUSH2_KO 0
+#endif
+#ifdef PUSH2_KO_RT
+#define CPIC_KO(bit) (a.ko & (bit))
+#else
+#define CPIC_KO(bit) (PUSH2_KO & (bit))
+#endif
 
 // ---------------------------------------------------------------------------------------
 // The 12 quadrant currents of one streak.  Reference: CALC_J, src/push.h:218-232 and
@@ -320,6 +336,8 @@ template <class R, bool FMA, int DEPOSIT, bool STATS, class List, bool OUTOFPLAC
 __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int first, int count,
                                              int lane, unsigned long long& n_cross, unsigned long long (&n_wrap)[6]) {
     const int m = first + lane;
+    bool leaves = false;
+    unsigned leaver = 0;
     if (lane < count) {
         R px = ml.x[m], py = ml.y[m], pz = ml.z[m];
         R dx = ml.rx[m], dy = ml.ry[m], dz = ml.rz[m];
@@ -331,8 +349,10 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
             const int axis = mover_streak(px, py, pz, dx, dy, dz, qq, sx, sy, sz, mx, my, mz, v5, dirv);
             R jc[12];
             streak_currents<FMA>(qq, sx, sy, sz, mx, my, mz, v5, jc);
-            if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)c * 12, jc);
-            else row_add_vec(a.acc + (long long)c * 12, jc);
+            if (!CPIC_KO(64)) {
+                if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)c * 12, jc);
+                else row_add_vec(a.acc + (long long)c * 12, jc);
+            } else if (jc[0] == R(-123.25)) a.acc[0] = jc[5];      // (keeps the arithmetic alive)
             if (axis == 3) break;
             // snap onto the face, move to the neighbour, re-enter from its other side
             const int code = cross_face(c, axis, dirv, a);
@@ -346,11 +366,11 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
         }
         const long long pn = ml.idx[m];
         (void)c_in;
-        if (a.leave_list && (c < a.leave_lo || c >= a.leave_hi)) {
-            const unsigned j = atomicAdd(a.leave_count, 1u);
-            if (j < a.leave_cap) a.leave_list[j] = (unsigned)pn;
-        }
-        if constexpr (OUTOFPLACE) {
+        leaves = a.leave_list && (c < a.leave_lo || c >= a.leave_hi);
+        leaver = (unsigned)pn;
+        if (CPIC_KO(128)) {
+            if (px == R(-123.25)) a.dst.store_pos(pn, px, py, pz, c);
+        } else if constexpr (OUTOFPLACE) {
             a.dst.store_pos(pn, px, py, pz, c);
             atomicAdd(a.hist + c, 1u);
         } else {
@@ -359,6 +379,16 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
         }
     }
     __syncwarp();
+    if (a.leave_list) {      // slab mode: list the particles left in a z ghost plane, one counter atomic per warp
+        const unsigned lm = __ballot_sync(0xffffffffu, leaves);
+        if (lm) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(a.leave_count, (unsigned)__popc(lm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned j = base + __popc(lm & ((1u << lane) - 1u));
+            if (leaves && j < a.leave_cap) a.leave_list[j] = leaver;
+        }
+    }
 }
 
 template <class R, bool FMA, int DEPOSIT, bool STATS, bool PREFETCH>

@@ -93,6 +93,7 @@ class GpuEngine:
         self._acc = torch.as_tensor(_DevArray(ptr, (self.gz, self.plane * 12), ts), device=self.device)
         self.push_ms = 0.0
         self.profile_push = False
+        self._push_events = []
 
     # views ---------------------------------------------------------------------------
     def field_planes(self, m):
@@ -111,7 +112,34 @@ class GpuEngine:
 
     def push_reorder(self, k):
         """push + cell ordering of the store in one pass (cpic_push_reorder)"""
-        self.ctx.push_reorder(k)
+        if self.profile_push and self.async_migration:      # no host wait: events now, elapsed times at the end
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            self.ctx.push_reorder(k)
+            ev1.record()
+            self._push_events.append((ev0, ev1))
+        else:
+            self.ctx.push_reorder(k)
+
+    def collect_push_ms(self):
+        """device time of the pushes recorded since profiling was switched on (synchronises)"""
+        if self._push_events:
+            torch.cuda.synchronize(self.device)
+            self.push_ms += sum(a.elapsed_time(b) for a, b in self._push_events)
+            self._push_events = []
+        return self.push_ms
+
+    # migration with the counts on the device (cpic_slab_extract_async / cpic_slab_append_async): float
+    # reordering push only
+    @property
+    def async_migration(self):
+        return self.real.itemsize == 4
+
+    def extract_async(self, lo, hi, cap, counts, rebase_lo, rebase_hi):
+        self.ctx.slab_extract_async(lo.data_ptr(), hi.data_ptr(), cap, counts.data_ptr(), rebase_lo, rebase_hi)
+
+    def append_async(self, buf, cap, count):
+        self.ctx.slab_append_async(buf.data_ptr(), cap, count.data_ptr())
 
     def unload_accumulator(self, k): self.ctx.unload_accumulator_array(k)
     def fold_phase(self, phase): self.ctx.update_ghosts(3 + phase)
@@ -132,7 +160,7 @@ class GpuEngine:
 
     def extract_z_leavers(self, lo, hi, cap, rebase_lo, rebase_hi):
         n = self.ctx.extract_z_leavers(lo.data_ptr(), hi.data_ptr(), cap, rebase_lo, rebase_hi)
-        if self.profile_push:          # extract synchronises: the push of this step has finished
+        if self.profile_push and not self._push_events:   # extract synchronises: the push of this step has finished
             self.push_ms += self.ctx.last_ms(0)
         return n
 
@@ -161,6 +189,23 @@ def _ring_exchange(send_up, send_down, recv_from_down, recv_from_up, up, down, r
         w.wait()
 
 
+def _ring_exchange_many(items, up, down, rank):
+    """items: (send_up, send_down, recv_from_down, recv_from_up) tuples, all in ONE batch of point-to-point
+    operations (same pairing rule as _ring_exchange, item after item)."""
+    if up == rank:
+        for su, sd, rd, ru in items:
+            rd.copy_(su)
+            ru.copy_(sd)
+        return
+    ops = []
+    for su, sd, _, _ in items:
+        ops += [dist.P2POp(dist.isend, su, up), dist.P2POp(dist.isend, sd, down)]
+    for _, _, rd, ru in items:
+        ops += [dist.P2POp(dist.irecv, rd, down), dist.P2POp(dist.irecv, ru, up)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
 def _pack(buf, cap, n, rbytes):
     """first n particles of a capacity-`cap` SoA send buffer -> contiguous bytes (same layout, capacity n)"""
     parts = [buf[m * cap * rbytes: m * cap * rbytes + n * rbytes] for m in range(7)]
@@ -185,11 +230,34 @@ class SlabStepper:
         # plane 1; my ghost plane 0 is the lower neighbour's plane nzl_down
         self.rebase_hi = -e.nz * e.plane
         self.rebase_lo = nzl_down * e.plane
-        self.migrated = [0, 0]          # particles sent down / up over the runner's life
-        self.last_migration = (0, 0)
+        self._migrated = [0, 0]         # particles sent down / up over the runner's life
+        self._last_migration = (0, 0)
+        # device-counted migration (no host synchronisation inside a step): used by fused steps when the engine has it
+        self.async_ok = bool(getattr(e, "async_migration", False))
+        if self.async_ok:
+            dev = self.send_lo.device
+            self.recv_dn, self.recv_up = e.alloc_bytes(nb), e.alloc_bytes(nb)
+            self.cnt_send = torch.zeros(2, dtype=torch.int64, device=dev)     # (n_lo, n_hi) of the last extraction
+            self.cnt_recv = torch.zeros(2, dtype=torch.int64, device=dev)     # (from the lower, from the upper neighbour)
+            self.cnt_total = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._async_used = False
+        self._last_async = False
         R = engine.real.type
         self.half = (float(R(0.5) * R(k.px)), float(R(0.5) * R(k.py)), float(R(0.5) * R(k.pz)))
         self.nsteps = 0
+
+    @property
+    def migrated(self):
+        if self.async_ok and self._async_used:
+            t = self.cnt_total.tolist()
+            return [self._migrated[0] + int(t[0]), self._migrated[1] + int(t[1])]
+        return self._migrated
+
+    @property
+    def last_migration(self):
+        if self.async_ok and self._async_used and self._last_async:
+            return tuple(int(v) for v in self.cnt_send.tolist())
+        return self._last_migration
 
     # -- pieces -----------------------------------------------------------------------
     def _exchange_planes(self, members, src_up, src_down, dst_from_down, dst_from_up, add=False):
@@ -224,9 +292,10 @@ class SlabStepper:
     def _migrate(self):
         e = self.e
         n_lo, n_hi = e.extract_z_leavers(self.send_lo, self.send_hi, self.cap, self.rebase_lo, self.rebase_hi)
-        self.last_migration = (n_lo, n_hi)
-        self.migrated[0] += n_lo
-        self.migrated[1] += n_hi
+        self._last_migration = (n_lo, n_hi)
+        self._last_async = False
+        self._migrated[0] += n_lo
+        self._migrated[1] += n_hi
         dev = self.send_lo.device
         cnt_s_up = torch.tensor([n_hi], dtype=torch.int64, device=dev)
         cnt_s_dn = torch.tensor([n_lo], dtype=torch.int64, device=dev)
@@ -251,6 +320,29 @@ class SlabStepper:
                     w.wait()
         e.append(r_dn, m_dn, m_dn)
         e.append(r_up, m_up, m_up)
+
+    def _exchange_after_push_async(self):
+        """Ghost accumulator planes + migrating particles in ONE batch of sends/receives, every count on the
+        device: nothing here waits for the push on the host, so the host enqueues the rest of the step (and
+        the next steps) while the push is still running.  Particle payloads travel as whole capacity-sized
+        buffers with their counts alongside."""
+        e = self.e
+        A = e.acc_planes()
+        nz = e.nz
+        e.extract_async(self.send_lo, self.send_hi, self.cap, self.cnt_send, self.rebase_lo, self.rebase_hi)
+        a_dn, a_up = torch.empty_like(A[0]), torch.empty_like(A[0])
+        _ring_exchange_many([(A[nz + 1], A[0], a_dn, a_up),
+                             (self.cnt_send[1:2], self.cnt_send[0:1], self.cnt_recv[0:1], self.cnt_recv[1:2]),
+                             (self.send_hi, self.send_lo, self.recv_dn, self.recv_up)], self.up, self.down, self.rank)
+        A[1] += a_dn            # the lower neighbour's high ghost plane is my plane 1
+        A[nz] += a_up           # the upper neighbour's low ghost plane is my plane nz
+        A[0].zero_()
+        A[nz + 1].zero_()
+        e.append_async(self.recv_dn, self.cap, self.cnt_recv[0:1])
+        e.append_async(self.recv_up, self.cap, self.cnt_recv[1:2])
+        self.cnt_total += self.cnt_send
+        self._async_used = True
+        self._last_async = True
 
     def _advance_b(self):
         e = self.e
@@ -298,10 +390,14 @@ class SlabStepper:
         else:
             e.push(k)
         t("push")
-        self._exchange_accumulators()
-        t("acc exchange")
-        self._migrate()
-        t("migrate")
+        if fused and self.async_ok:
+            self._exchange_after_push_async()
+            t("acc exchange + migrate (async)")
+        else:
+            self._exchange_accumulators()
+            t("acc exchange")
+            self._migrate()
+            t("migrate")
         e.unload_accumulator(k)
         self._advance_b()
         self._advance_e()
@@ -391,7 +487,7 @@ class _BenchRunner:
         self.eng.push_ms = 0.0
 
     def profile_result(self):
-        return {"push_ms": self.eng.push_ms, "steps": 0}
+        return {"push_ms": self.eng.collect_push_ms(), "steps": 0}
 
     def device_ms(self):
         return self.t_ms
@@ -467,7 +563,9 @@ class SlabBench(_BenchRunner):
         self.eng = GpuEngine(d.nx, d.ny, nzl, cap, real=d.real, device=self.local, fp_mode=self.fp,
                              z_periodic=self.world == 1)
         self.eng.ctx.init_uniform_plasma(z0 * per_plane, n_local, d.nx, d.ny, d.nz, d.nppc, z0=z0, weight=self.we)
-        send_cap = max(4096, int(per_plane * 0.10))      # ~2.3 % of a plane's particles cross a face per step
+        # ~2.3 % of a plane's particles cross a z face per step in this plasma (vth = 0.1 c, dt = 0.99 Courant);
+        # the exchange buffers travel whole, so the capacity is kept near 2x that (an overflow is reported)
+        send_cap = max(4096, int(per_plane * 0.05))
         nzl_down = ranges[(self.rank - 1) % self.world][1]
         nzl_up = ranges[(self.rank + 1) % self.world][1]
         self.stepper = SlabStepper(self.eng, self.k, self.rank, self.world, nzl_down, nzl_up, send_cap)

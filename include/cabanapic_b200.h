@@ -204,6 +204,17 @@ int  cpic_advance_e_stencil(cpic_ctx* ctx, double px, double py, double pz, doub
 int  cpic_extract_z_leavers(cpic_ctx* ctx, void* lo_buf, void* hi_buf, int64_t capacity, int64_t* n_lo, int64_t* n_hi,
                             int32_t rebase_lo, int32_t rebase_hi);
 int  cpic_append_particles_device(cpic_ctx* ctx, const void* buf, int64_t capacity, int64_t n);
+/* The same migration with every count kept ON THE DEVICE, so that the host never waits for the push and can
+ * enqueue steps ahead (float reordering push only; CPIC_E_UNSUPPORTED otherwise).  extract: as
+ * cpic_extract_z_leavers (leaver list of the last cpic_push_reorder), the two counts (n_lo, n_hi) are written
+ * to counts_dev, int64[2] in DEVICE memory, for the caller to send along with the whole capacity-sized
+ * buffers.  append: *count_dev (device) particles of a received buffer join the store.  The context's own
+ * particle count lives on the device from the first extract on; any entry point that needs it on the host
+ * (cpic_num_particles, downloads, cpic_push, cpic_sort_particles, ...) synchronises once and reports capacity
+ * overflows that happened in between as CPIC_E_CAPACITY. */
+int  cpic_slab_extract_async(cpic_ctx* ctx, void* lo_buf, void* hi_buf, int64_t capacity, int64_t* counts_dev,
+                             int32_t rebase_lo, int32_t rebase_hi);
+int  cpic_slab_append_async(cpic_ctx* ctx, const void* buf, int64_t capacity, const int64_t* count_dev);
 
 /* Device-side timing of the last call of each kind, in milliseconds (CUDA events on the
  * context's stream).  what: 0 push, 1 sort, 2 field side (interp+unload+advance), 3 step total. */

@@ -572,6 +572,57 @@ def test_slab_stepper_fused_reorder_keeps_histogram_through_migration():
     assert (np.abs(f1 - f0) / scale)[:6].max() < 1e-4
 
 
+def test_slab_async_migration_counts_and_overflow():
+    """cpic_slab_extract_async / cpic_slab_append_async (every count on the device, no host round trip) against
+    the synchronising cpic_extract_z_leavers on the same states: same leaver counts, same particles left behind,
+    same store after the arrivals are appended; a send-buffer overflow surfaces as CPIC_E_CAPACITY at the next
+    call that needs the host's particle count."""
+    import torch
+    from cabanapic_b200.dist import GpuEngine
+    m = cp()
+    nx, ny, nz, prec = 6, 5, 4, "f32"
+    s = random_state(nx, ny, nz, nppc=30, prec=prec, seed=9)
+    k = to_k(consts_for(nx, ny, nz, prec))
+    plane = (nx + 2) * (ny + 2)
+    cap = s.np
+    res = []
+    for mode in ("sync", "async"):
+        e = GpuEngine(nx, ny, nz, s.np + 100, real=np.float32, z_periodic=False)
+        try:
+            c = e.ctx
+            c.upload_particles(s.p); c.upload_fields(s.f)
+            lo, hi = e.alloc_bytes(cap * 32), e.alloc_bytes(cap * 32)
+            cnt = torch.zeros(2, dtype=torch.int64, device=lo.device)
+            counts = []
+            for it in range(3):
+                c.load_interpolator_array(); c.clear_accumulator_array(); c.push_reorder(k)
+                if mode == "sync":
+                    n_lo, n_hi = c.extract_z_leavers(lo.data_ptr(), hi.data_ptr(), cap, nz * plane, -nz * plane)
+                    c.append_particles_device(lo.data_ptr(), cap, n_lo)      # periodic with itself: they come back
+                    c.append_particles_device(hi.data_ptr(), cap, n_hi)
+                else:
+                    c.slab_extract_async(lo.data_ptr(), hi.data_ptr(), cap, cnt.data_ptr(), nz * plane, -nz * plane)
+                    c.slab_append_async(lo.data_ptr(), cap, cnt[0:1].data_ptr())
+                    c.slab_append_async(hi.data_ptr(), cap, cnt[1:2].data_ptr())
+                    n_lo, n_hi = cnt.tolist()
+                counts.append((n_lo, n_hi))
+            assert c.num_particles == s.np
+            res.append((counts, c.download_particles()))
+            if mode == "async":          # overflow of a 2-particle send buffer on a device-counted extraction
+                c.load_interpolator_array(); c.clear_accumulator_array(); c.push_reorder(k)
+                c.slab_extract_async(lo.data_ptr(), hi.data_ptr(), 2, cnt.data_ptr(), nz * plane, -nz * plane)
+                with pytest.raises(m.CpicError) as err:
+                    c.num_particles
+                assert err.value.code == -4
+        finally:
+            e.close()
+    (c0, p0), (c1, p1) = res
+    assert c0 == c1 and all(a > 0 and b > 0 for a, b in c0)
+    a, b = canonical_order(p0), canonical_order(p1)
+    for n in PARTICLE_NAMES:
+        assert np.array_equal(p0[n][a], p1[n][b]), n
+
+
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 @pytest.mark.parametrize("interval", [1, 2, 3, -1])
 def test_sorted_steps_match_unsorted_oracle(prec, interval):
