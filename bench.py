@@ -219,6 +219,8 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         runner.step(1, sort_interval)
+    if hasattr(runner, "prepare_timed"):
+        runner.prepare_timed(sort_interval)      # multi-GPU: capture two steps into a CUDA graph
     barrier()
     runner.profile(True)
     sampler = ClockSampler(local)
@@ -287,6 +289,8 @@ def run_ours(args):
                            "l2": "inputs (>= 30 GB per GPU) exceed the 126 MB L2; no flush needed"},
                 "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
                 "roofline": roofline}
+        if getattr(runner, "host_ms", 0.0):
+            line["host_enqueue_ms_per_step"] = runner.host_ms / args.steps
         if e2e is not None:
             e2e.pop("seconds", None)
             line["e2e"] = e2e
@@ -294,7 +298,17 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # never let a teardown problem (e.g. a communicator still referenced by a captured graph) hang the run:
+        # the result is printed; give destroy_process_group a few seconds, then leave
+        sys.stdout.flush()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            killer.cancel()
 
 
 class SingleGpu:

@@ -72,15 +72,18 @@ class GpuEngine:
     """The engine interface over one ``Context`` (C ABI).  ``nz`` is the local slab thickness."""
 
     def __init__(self, nx, ny, nz, max_particles, real=np.float32, device=0, fp_mode=_lib.FP_STRICT,
-                 z_periodic=True, solver=_lib.SOLVER_EM):
+                 z_periodic=True, solver=_lib.SOLVER_EM, stream=None):
         self.nx, self.ny, self.nz = nx, ny, nz
         self.real = np.dtype(real)
         self.tdtype = torch.float32 if self.real.itemsize == 4 else torch.float64
         self.device = torch.device("cuda", device)
         self.ctx = Context(nx, ny, nz, 1, max_particles=max_particles, real=real, device=device, fp_mode=fp_mode,
                            enable_sort=True, solver=solver)
-        # all work of this rank -- our kernels, torch's plane ops, NCCL -- is ordered on torch's stream
-        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # all work of this rank -- our kernels, torch's plane ops, NCCL -- is ordered on ONE torch stream: the
+        # current one, or `stream` (the caller then runs everything under torch.cuda.stream(stream); a side
+        # stream is what CUDA-graph capture of whole steps needs)
+        self.stream = stream
+        self.ctx.set_stream((stream or torch.cuda.current_stream(self.device)).cuda_stream)
         if not z_periodic:
             self.ctx.set_axis_periodic(1, 1, 0)
         self.gx, self.gy, self.gz = nx + 2, ny + 2, nz + 2
@@ -472,22 +475,87 @@ class _BenchRunner:
         self.l0 = 0
         self.t_ms = 0.0
 
+    # Multi-GPU steps are short (4 ms at 8 GPUs) and made of ~120 host calls (torch plane ops, NCCL groups, our
+    # launches): with the slab exchange free of host synchronisation (cpic_slab_*_async) a PAIR of steps -- the
+    # particle double buffer is back where it started after two -- is captured into one CUDA graph and replayed.
+    graph = None
+    used_graph = False
+    graph_launches = 0
+    host_ms = 0.0
+    last_n = 0
+    _stream = None
+
+    def _on_stream(self):
+        import contextlib
+        return torch.cuda.stream(self._stream) if self._stream is not None else contextlib.nullcontext()
+
+    def prepare_timed(self, sort_interval):
+        """called once after the warm-up steps: capture two fused steps (falls back to eager launches on any error)"""
+        import os
+        st = self.stepper
+        if (self.graph is not None or self._stream is None or sort_interval >= 0 or os.environ.get("CPIC_NO_GRAPH")
+                or not getattr(st, "async_ok", False) or not getattr(st, "_async_used", False)):
+            return
+        keep = self.eng.profile_push
+        self.eng.profile_push = False
+        try:
+            torch.cuda.synchronize()
+            l0 = self.eng.ctx.launch_count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                st.step(fused=True)
+                st.step(fused=True)
+            st.nsteps -= 2                       # captured, not executed
+            self.graph_launches = self.eng.ctx.launch_count - l0
+            self.graph = g
+            self.used_graph = True
+        except Exception as ex:                  # pragma: no cover - depends on the NCCL / driver at hand
+            import sys
+            print(f"[rank {self.rank}] CUDA-graph capture of the slab step failed, running eagerly: {ex}", file=sys.stderr, flush=True)
+            self.graph = None
+            torch.cuda.synchronize()
+        self.eng.profile_push = keep
+
     def step(self, n, sort_interval):
         self.l0 = self.eng.ctx.launch_count
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for s in range(n):
-            self.stepper.step(sort=sort_interval > 0 and s % sort_interval == 0, fused=sort_interval < 0)
-        ev1.record()
-        torch.cuda.synchronize()
-        self.t_ms = ev0.elapsed_time(ev1)
+        self.last_n = n
+        with self._on_stream():
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record()
+            s = 0
+            if self.graph is not None and sort_interval < 0:
+                while s + 2 <= n:
+                    self.graph.replay()
+                    s += 2
+                self.stepper.nsteps += s
+                self.l0 -= self.graph_launches * (s // 2)
+            keep = self.eng.profile_push
+            if self.graph is not None:
+                self.eng.profile_push = False          # (push times come from an eager pass, profile_result)
+            for s in range(s, n):
+                self.stepper.step(sort=sort_interval > 0 and s % sort_interval == 0, fused=sort_interval < 0)
+            self.eng.profile_push = keep
+            ev1.record()
+            self.host_ms = (time.perf_counter() - t0) * 1e3
+            torch.cuda.synchronize()
+            self.t_ms = ev0.elapsed_time(ev1)
 
     def profile(self, on):
         self.eng.profile_push = bool(on)
         self.eng.push_ms = 0.0
 
     def profile_result(self):
-        return {"push_ms": self.eng.collect_push_ms(), "steps": 0}
+        if self.graph is not None and self.eng.profile_push:
+            # the timed region replayed a graph: time the same push kernel over a few eager steps right after it
+            with self._on_stream():
+                self.eng.push_ms = 0.0
+                for _ in range(4):
+                    self.stepper.step(fused=True)
+                ms = self.eng.collect_push_ms() / 4
+            return {"push_ms": ms * max(self.last_n, 1), "steps": 0, "push_timing": "4 eager steps after the graph-replayed timed region"}
+        with self._on_stream():
+            return {"push_ms": self.eng.collect_push_ms(), "steps": 0}
 
     def device_ms(self):
         return self.t_ms
@@ -526,14 +594,15 @@ class _BenchRunner:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for s in range(steps):
-            c._ck(L.cpic_upload_particles(c.h, *up, n))
-            c._ck(L.cpic_upload_fields(c.h, fptr))
-            self.stepper.step(sort=sort_interval > 0, fused=sort_interval < 0)
-            c._ck(L.cpic_download_particles(c.h, *dn, cap2, C.byref(got)))
-            c._ck(L.cpic_download_fields(c.h, fptr))
-        if self.world > 1:
-            dist.barrier()
+        with self._on_stream():
+            for s in range(steps):
+                c._ck(L.cpic_upload_particles(c.h, *up, n))
+                c._ck(L.cpic_upload_fields(c.h, fptr))
+                self.stepper.step(sort=sort_interval > 0, fused=sort_interval < 0)
+                c._ck(L.cpic_download_particles(c.h, *dn, cap2, C.byref(got)))
+                c._ck(L.cpic_download_fields(c.h, fptr))
+            if self.world > 1:
+                dist.barrier()
         torch.cuda.synchronize()
         sec = time.perf_counter() - t0
         return {"value": self.d.num_particles * steps / sec, "unit": "particle-steps/s",
@@ -543,6 +612,12 @@ class _BenchRunner:
                         "exchanges, D2H local particles+fields; bytes summed over ranks"}
 
     def close(self):
+        if self.graph is not None:           # the graph references NCCL work: release it before the communicator goes
+            torch.cuda.synchronize()
+            self.graph = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
         rep = getattr(self.stepper, "profile_report", lambda: None)()
         if rep and self.rank == 0:
             import sys
@@ -560,19 +635,23 @@ class SlabBench(_BenchRunner):
         per_plane = d.nx * d.ny * d.nppc
         n_local = per_plane * nzl
         cap = int(n_local * 1.10) + 4096
-        self.eng = GpuEngine(d.nx, d.ny, nzl, cap, real=d.real, device=self.local, fp_mode=self.fp,
-                             z_periodic=self.world == 1)
-        self.eng.ctx.init_uniform_plasma(z0 * per_plane, n_local, d.nx, d.ny, d.nz, d.nppc, z0=z0, weight=self.we)
+        self._stream = torch.cuda.Stream(device=self.local)
+        with self._on_stream():
+            self.eng = GpuEngine(d.nx, d.ny, nzl, cap, real=d.real, device=self.local, fp_mode=self.fp,
+                                 z_periodic=self.world == 1, stream=self._stream)
+            self.eng.ctx.init_uniform_plasma(z0 * per_plane, n_local, d.nx, d.ny, d.nz, d.nppc, z0=z0, weight=self.we)
         # ~2.3 % of a plane's particles cross a z face per step in this plasma (vth = 0.1 c, dt = 0.99 Courant);
         # the exchange buffers travel whole, so the capacity is kept near 2x that (an overflow is reported)
         send_cap = max(4096, int(per_plane * 0.05))
         nzl_down = ranges[(self.rank - 1) % self.world][1]
         nzl_up = ranges[(self.rank + 1) % self.world][1]
-        self.stepper = SlabStepper(self.eng, self.k, self.rank, self.world, nzl_down, nzl_up, send_cap)
+        with self._on_stream():
+            self.stepper = SlabStepper(self.eng, self.k, self.rank, self.world, nzl_down, nzl_up, send_cap)
         self.eng.sync()
 
     def describe(self):
-        return f"{self.world} z-slabs (NCCL ghost-plane exchange + particle migration)"
+        how = "two steps per CUDA-graph replay" if self.used_graph else "eager launches"
+        return f"{self.world} z-slabs (NCCL ghost-plane exchange + particle migration, {how})"
 
 
 class ReplicatedBench(_BenchRunner):
