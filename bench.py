@@ -77,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -105,7 +105,14 @@ class ClockSampler:
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
+        pw = []
+        for r in self.rows:
+            try:
+                pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_mhz_min": min(sm) if sm else None, "power_w_max": max(pw) if pw else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 

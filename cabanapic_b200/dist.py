@@ -628,6 +628,8 @@ class _BenchRunner:
 
 
 class SlabBench(_BenchRunner):
+    open_z = False      # tests: keep the z exchange (with itself) even on one rank
+
     def setup(self):
         d = self.d
         z0, nzl = slab_ranges(d.nz, self.world)[self.rank]
@@ -638,7 +640,7 @@ class SlabBench(_BenchRunner):
         self._stream = torch.cuda.Stream(device=self.local)
         with self._on_stream():
             self.eng = GpuEngine(d.nx, d.ny, nzl, cap, real=d.real, device=self.local, fp_mode=self.fp,
-                                 z_periodic=self.world == 1, stream=self._stream)
+                                 z_periodic=self.world == 1 and not self.open_z, stream=self._stream)
             self.eng.ctx.init_uniform_plasma(z0 * per_plane, n_local, d.nx, d.ny, d.nz, d.nppc, z0=z0, weight=self.we)
         # ~2.3 % of a plane's particles cross a z face per step in this plasma (vth = 0.1 c, dt = 0.99 Courant);
         # the exchange buffers travel whole, so the capacity is kept near 2x that (an overflow is reported)
