@@ -171,6 +171,7 @@ struct Ctx final : CtxBase {
         if (const char* e = getenv("CPIC_PUSH_GRID")) push_grid = atoi(e);
         if (const char* e = getenv("CPIC_PUSH_V1")) use_push2 = atoi(e) == 0;
         if (const char* e = getenv("CPIC_PUSH2_FASTDS")) push2_fastds = atoi(e) != 0;
+        if (const char* e = getenv("CPIC_PUSH2_PRIV")) push2_priv = atoi(e) != 0;
         if (const char* e = getenv("CPIC_DEP_THRESH")) dep_thresh = atoi(e);
         if (const char* e = getenv("CPIC_DEP_ROUNDS")) dep_rounds = atoi(e);
         nc_pad = (g.nc + 63) / 64 * 64;
@@ -584,16 +585,26 @@ struct Ctx final : CtxBase {
     }
     // second-generation float kernel (packed FP32x2, two particles per thread); deposit mode WARP only
     bool use_push2 = true, push2_fastds = true;
+    // Grids of up to PRIV_MAX_CELLS cells (the reference's 1-D decks: 34 x 3 x 3 = 306): every block keeps a private
+    // accumulator + histogram in shared memory -- a global reduction per streak would serialise the whole machine
+    // on a few hundred L2 lines (BASELINE configs[1], 1e8 particles on 32 cells: 86 -> ms/step, profiles/r03_*c2*)
+    static constexpr long long PRIV_MAX_CELLS = 1024;
+    bool push2_priv = true;
+    bool use_priv() const { return push2_priv && g.nc <= PRIV_MAX_CELLS; }
     template <bool FMA, bool ST, bool FD>
     int launch_push2(const PushArgs<float>& a) {
+        if (!ST && a.priv_nc > 0) return a.hist ? launch_push2h<FMA, ST, FD, true, false, true>(a) : launch_push2h<FMA, ST, FD, false, false, true>(a);
         return a.hist ? launch_push2h<FMA, ST, FD, true>(a) : launch_push2h<FMA, ST, FD, false>(a);
     }
     template <bool FMA, bool ST, bool FD>
-    int launch_push2r(const PushArgs<float>& a) { return launch_push2h<FMA, ST, FD, true, true>(a); }
-    template <bool FMA, bool ST, bool FD, bool H, bool RE = false>
+    int launch_push2r(const PushArgs<float>& a) {
+        if (!ST && a.priv_nc > 0) return launch_push2h<FMA, ST, FD, true, true, true>(a);
+        return launch_push2h<FMA, ST, FD, true, true>(a);
+    }
+    template <bool FMA, bool ST, bool FD, bool H, bool RE = false, bool PV = false>
     int launch_push2h(const PushArgs<float>& a) {
-        auto kern = k_push2<FMA, ST, FD, H, RE>;
-        const size_t smem = sizeof(Push2Smem);
+        auto kern = k_push2<FMA, ST, FD, H, RE, PV>;
+        const size_t smem = sizeof(Push2Smem) + (PV ? (size_t)a.priv_nc * 13 * sizeof(float) : 0);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PUSH2_WARPS * 32, smem);
@@ -678,6 +689,7 @@ struct Ctx final : CtxBase {
         a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         a.np_dev = nullptr;
+        a.priv_nc = use_priv() ? (int)g.nc : 0;
         a.ko = 0;
 #ifdef PUSH2_KO_RT
         if (const char* e = getenv("CPIC_PUSH2_KO")) a.ko = atoi(e);
@@ -687,7 +699,7 @@ struct Ctx final : CtxBase {
     int push(const cpic_consts& k) override {
         if (np == 0) return CPIC_OK;
         PushArgs<R> a;
-        a.ko = 0; a.np_dev = nullptr;
+        a.ko = 0; a.np_dev = nullptr; a.priv_nc = use_priv() ? (int)g.nc : 0;
         a.dst = P[cur]; a.cursor = nullptr;
         a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
         a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;

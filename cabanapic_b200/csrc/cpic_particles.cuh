@@ -46,6 +46,7 @@ struct PushArgs {
     unsigned* leave_count;
     unsigned leave_cap;
     int leave_lo, leave_hi;
+    int priv_nc;               // > 0: k_push2<PRIV> keeps a block-private accumulator (+ histogram) of this many cells in shared memory
     const long long* np_dev;   // optional: the particle count lives on the device (overrides np; k_push2 only)
     int ko;   // developer knock-out mask (timing studies; honoured only by builds with -DPUSH2_KO_RT, see cpic_push2.cuh)
 };
@@ -124,6 +125,22 @@ __device__ __forceinline__ void row_add_vec(float* row, const float (&a)[12]) {
     red_add_v4(row + 8, a[8], a[9], a[10], a[11]);
 }
 __device__ __forceinline__ void row_add_vec(double* row, const double (&a)[12]) { row_add_scalar(row, a); }
+// Deposit target of k_push2: the global accumulator (one 128-bit reduction), or -- PRIV, grids of a few hundred
+// cells where every reduction of the machine would hit the same handful of L2 lines -- a block-private copy in
+// shared memory that is added to the global one once, when the block retires.
+template <bool PRIV>
+__device__ __forceinline__ void acc_add4(float* __restrict__ gacc, float* sacc, int c, int eg, float x, float y, float z, float w) {
+    if constexpr (PRIV) {
+        float* p = sacc + c * 12 + eg * 4;
+        atomicAdd(p + 0, x); atomicAdd(p + 1, y); atomicAdd(p + 2, z); atomicAdd(p + 3, w);
+    } else {
+        red_add_v4(gacc + (long long)c * 12 + eg * 4, x, y, z, w);
+    }
+}
+template <bool PRIV>
+__device__ __forceinline__ void hist_add(unsigned* __restrict__ ghist, unsigned* shist, int c, unsigned v) {
+    if constexpr (PRIV) atomicAdd(shist + c, v); else atomicAdd(ghist + c, v);
+}
 
 // Sum a[0..11] over the lanes in `mask`-selected contributions (others pass zeros) with a
 // transpose-reduce: after the 5 exchange stages lane L holds the warp total of entry
@@ -332,9 +349,10 @@ struct WarpMoverList {
 // src/move_p.h:93-371 -- streak, deposit into the current cell, then either stop (end of
 // track) or cross the face into the neighbour and continue.
 // OUTOFPLACE: the list's idx are slots of a.dst (reordering push) and the cell is always written.
-template <class R, bool FMA, int DEPOSIT, bool STATS, class List, bool OUTOFPLACE = false>
+template <class R, bool FMA, int DEPOSIT, bool STATS, class List, bool OUTOFPLACE = false, bool PRIV = false>
 __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int first, int count,
-                                             int lane, unsigned long long& n_cross, unsigned long long (&n_wrap)[6]) {
+                                             int lane, unsigned long long& n_cross, unsigned long long (&n_wrap)[6],
+                                             float* sacc = nullptr, unsigned* shist = nullptr) {
     const int m = first + lane;
     bool leaves = false;
     unsigned leaver = 0;
@@ -350,7 +368,11 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
             R jc[12];
             streak_currents<FMA>(qq, sx, sy, sz, mx, my, mz, v5, jc);
             if (!CPIC_KO(64)) {
-                if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)c * 12, jc);
+                if constexpr (PRIV) {
+                    acc_add4<true>(nullptr, sacc, c, 0, (float)jc[0], (float)jc[1], (float)jc[2], (float)jc[3]);
+                    acc_add4<true>(nullptr, sacc, c, 1, (float)jc[4], (float)jc[5], (float)jc[6], (float)jc[7]);
+                    acc_add4<true>(nullptr, sacc, c, 2, (float)jc[8], (float)jc[9], (float)jc[10], (float)jc[11]);
+                } else if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)c * 12, jc);
                 else row_add_vec(a.acc + (long long)c * 12, jc);
             } else if (jc[0] == R(-123.25)) a.acc[0] = jc[5];      // (keeps the arithmetic alive)
             if (axis == 3) break;
@@ -372,10 +394,10 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
             if (px == R(-123.25)) a.dst.store_pos(pn, px, py, pz, c);
         } else if constexpr (OUTOFPLACE) {
             a.dst.store_pos(pn, px, py, pz, c);
-            atomicAdd(a.hist + c, 1u);
+            hist_add<PRIV>(a.hist, shist, c, 1u);
         } else {
             a.p.store_pos(pn, px, py, pz, c);
-            if (a.hist) atomicAdd(a.hist + c, 1u);
+            if (a.hist) hist_add<PRIV>(a.hist, shist, c, 1u);
         }
     }
     __syncwarp();
