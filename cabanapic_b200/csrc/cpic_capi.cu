@@ -99,6 +99,7 @@ struct CtxBase {
     virtual int slab_append_async(const void* buf, long long cap, const long long* count_dev) = 0;
     virtual bool few_cells() const = 0;   // grid small enough for the block-private accumulator (k_push2<PRIV>)
     virtual int sync_np() = 0;      // device-count mode -> host-count mode (synchronises); no-op otherwise
+    long long fb_steps = 0;         // steps taken in the few-cells fallback of CPIC_SORT_FUSED (sort when % 8 == 0)
     bool dev_count = false;         // slab mode: np lives in dc[0] on the device, the host's np is stale
     virtual int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
                           const void* const fin[9], void* const fout[9], double* energies) = 0;
@@ -1094,15 +1095,16 @@ int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_
         // CPIC_SORT_FUSED = "keep the store cell-ordered the cheapest way": the reordering push, except on grids of a few
         // hundred cells, where its slot claims would serialise on a handful of cursors and a counting sort every 8
         // steps is 3x cheaper (BASELINE configs[1]: 16.1 vs 5.7 ms/step, profiles/r03_probe_c2_*)
-        if (sort_interval == CPIC_SORT_FUSED && c->few_cells()) sort_interval = 8;
-        const bool fused = sort_interval == CPIC_SORT_FUSED;
+        const bool fallback = sort_interval == CPIC_SORT_FUSED && c->few_cells();
+        const bool fused = sort_interval == CPIC_SORT_FUSED && !fallback;
         if (fused) rc = c->prepare_reorder();        // histogram (first step only) + scan of the cell counts
+        else if (fallback) { if (c->fb_steps++ % 8 == 0) rc = c->sort(); }      // (counted across calls: one-step calls too)
         else if (sort_interval > 0 && s % sort_interval == 0) rc = c->sort();
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 1], c->stream);
         if (!rc) rc = c->load_interpolator();
         if (!rc) rc = c->clear_accumulator();
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 2], c->stream);
-        c->want_hist = sort_interval > 0 && (s + 1) % sort_interval == 0;   // the next step starts with a sort
+        c->want_hist = fallback ? (c->fb_steps % 8 == 0) : (sort_interval > 0 && (s + 1) % sort_interval == 0);   // the next step starts with a sort
         if (!rc) rc = fused ? c->push_reorder(*k) : c->push(*k);
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 3], c->stream);
         if (!rc) rc = c->unload_accumulator(*k);
