@@ -391,6 +391,100 @@ def test_current_conservation_at_scale():
     assert np.abs(p1["dx"]).max() <= 1 and np.abs(p1["dy"]).max() <= 1 and np.abs(p1["dz"]).max() <= 1
 
 
+def test_full_size_c5_properties():
+    """BASELINE configs[4] at FULL size (256^3 cells x 64 ppc = 2^30 particles, 69 GB of particle store) through
+    size-independent properties, all evaluated on the device.  The weights are first made a tag (2^20 classes of
+    1024 particles, w = we*(1 + class/2^21); the push only ever multiplies w by the species charge).  After 4 steps
+    of the default (reordering) step: the particle count is unchanged, every cell index is an interior voxel, every
+    offset lies in [-1, 1], and the class histogram of the weights is unchanged -- no particle lost, duplicated or
+    torn by the out-of-place slot claims, which is what a wrong cell histogram or an overlapping segment would do.
+    Skipped down to the largest z extent the device's free memory allows."""
+    import torch
+    m = cp()
+    from cabanapic_b200 import decks
+    free, _ = torch.cuda.mem_get_info()
+    nz = 256
+    while nz > 16 and 256 * 256 * nz * 64 * 64 * 1.25 + 6e9 > free:
+        nz //= 2
+    if nz < 256:
+        print(f"(device memory allows only nz = {nz})")
+    d = decks.uniform_plasma(256, 256, nz, 64)
+    k, _, we = d.consts()
+    n = d.num_particles
+    NCLS = 1 << 20
+    chunk = 1 << 26
+
+    class _Dev:
+        def __init__(self, p, nwords):
+            self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<f4", "data": (int(p), False), "version": 2, "strides": None}
+
+    with m.Context(256, 256, nz, 1, max_particles=n, real=np.float32) as c:
+        c.init_uniform_plasma(0, n, 256, 256, nz, 64, weight=we)
+        c.upload_fields(d.initial_fields())
+        rec = lambda: torch.as_tensor(_Dev(c.device_ptr(0)[0], n * 8), device="cuda").view(n, 8)   # dx dy dz cell ux uy uz w
+        c.sync()
+        r = rec()
+        for first in range(0, n, chunk):
+            idx = torch.arange(first, min(first + chunk, n), device="cuda", dtype=torch.int64) % NCLS
+            r[first:first + chunk, 7] = (np.float32(we) * (1.0 + idx.to(torch.float64) / (2.0 * NCLS))).to(torch.float32)
+        torch.cuda.synchronize()
+
+        def classes():
+            r = rec()
+            h = torch.zeros(NCLS, dtype=torch.int64, device="cuda")
+            for first in range(0, n, chunk):
+                w = r[first:first + chunk, 7].to(torch.float64)
+                kcls = torch.round((w / float(np.float32(we)) - 1.0) * (2.0 * NCLS)).to(torch.int64)
+                assert int(kcls.min()) >= 0 and int(kcls.max()) < NCLS
+                h += torch.bincount(kcls, minlength=NCLS)
+            return h
+        h0 = classes()
+        assert int(h0.sum()) == n
+        c.step(k, 4, m.SORT_FUSED, False)
+        c.sync()
+        assert c.num_particles == n
+        r = rec()
+        gx, gy = 258, 258
+        for first in range(0, n, chunk):
+            rr = r[first:first + chunk]
+            cell = rr[:, 3].contiguous().view(torch.int32)
+            ix, iy, iz = cell % gx, (cell // gx) % gy, cell // (gx * gy)
+            assert int(ix.min()) >= 1 and int(ix.max()) <= 256 and int(iy.min()) >= 1 and int(iy.max()) <= 256
+            assert int(iz.min()) >= 1 and int(iz.max()) <= nz
+            assert float(rr[:, :3].abs().max()) <= 1.0
+            del cell, ix, iy, iz
+        assert torch.equal(classes(), h0)
+
+
+def test_full_size_c2_properties():
+    """BASELINE configs[1] at full size: the two-stream deck (decks/2stream-short.cxx physics, x-oriented
+    initialiser of decks/custom_init.cxx) scaled to 1e8 particles on 32 cells, ES field solver
+    (-DSOLVER_TYPE=ES), 24 steps of the default step (block-private accumulator; CPIC_SORT_FUSED resolves to the
+    periodic sort on such a grid).  Properties: particle count unchanged, every particle in an interior x cell with
+    its offset in [-1, 1], energies finite, no B energy (ES), and the field energy grows out of the deposit noise
+    (the two-stream instability) instead of staying at or blowing past it."""
+    m = cp()
+    from cabanapic_b200 import decks
+    d = decks.two_stream_short(np.float32, "x")
+    d.nppc = 3_125_000
+    sim = m.Simulation(d, solver=m.SOLVER_ES_1D)
+    try:
+        n = sim.ctx.num_particles
+        assert n == 100_000_000
+        en = sim.run(24, sort_interval=m.SORT_FUSED, energies=True)
+        assert np.all(np.isfinite(en)) and np.all(en[:, 1] == 0.0)
+        assert en[-1, 0] > 10 * en[0, 0] and en[-1, 0] < 1e-3
+        assert sim.ctx.num_particles == n
+        p = sim.particles()
+        ix = p["cell"] % (d.nx + 2)
+        assert ix.min() >= 1 and ix.max() <= d.nx
+        assert np.array_equal(p["cell"] // (d.nx + 2), np.full(n, 4, dtype=p["cell"].dtype))      # y = z = 1: (1 + 3*1)
+        for a_ in ("dx", "dy", "dz"):
+            assert np.abs(p[a_]).max() <= 1.0
+    finally:
+        sim.close()
+
+
 def test_energy_history_2stream_em_double_vs_gold():
     """The reference's regression test (tests/energy_comparison): 6000 steps of the 1x32x1 EM
     two-stream deck in double.  Reference criterion: < 10 % on lines 3581..4880.  Ours: the
