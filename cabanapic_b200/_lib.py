@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
             "cpic_advance_e": [vp, dbl, dbl, dbl, dbl],
             "cpic_uncenter_particles": [vp, dbl],
             "cpic_energies": [vp, C.POINTER(dbl), C.POINTER(dbl)],
+            "cpic_kinetic_energy": [vp, C.POINTER(dbl)],
             "cpic_update_ghosts": [vp, C.c_int],
             "cpic_step": [vp, C.POINTER(Consts), i64, i32, vp],
             "cpic_step_host": [vp, C.POINTER(Consts), C.POINTER(vp), C.POINTER(vp), i64, C.POINTER(vp), C.POINTER(vp), vp],
@@ -147,7 +148,7 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
             "cpic_upload_accumulators", "cpic_download_accumulators", "cpic_load_interpolator_array",
             "cpic_initialize_interpolator", "cpic_clear_accumulator_array", "cpic_push", "cpic_contribute",
             "cpic_unload_accumulator_array", "cpic_advance_b", "cpic_advance_e", "cpic_uncenter_particles",
-            "cpic_energies", "cpic_update_ghosts", "cpic_step", "cpic_step_host", "cpic_sort_particles", "cpic_push_reorder", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
+            "cpic_energies", "cpic_kinetic_energy", "cpic_update_ghosts", "cpic_step", "cpic_step_host", "cpic_sort_particles", "cpic_push_reorder", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
             "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
             "cpic_set_axis_periodic", "cpic_advance_b_stencil", "cpic_advance_e_stencil", "cpic_extract_z_leavers", "cpic_append_particles_device", "cpic_slab_extract_async", "cpic_slab_append_async",
             "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile"]
@@ -290,6 +291,12 @@ class Context:
         e, b = C.c_double(), C.c_double()
         self._ck(self.L.cpic_energies(self.h, C.byref(e), C.byref(b)))
         return e.value, b.value
+
+    def kinetic_energy(self):
+        """sum_p w_p (gamma_p - 1), in double (cpic_kinetic_energy)"""
+        v = C.c_double()
+        self._ck(self.L.cpic_kinetic_energy(self.h, C.byref(v)))
+        return v.value
 
     def step(self, k: Consts, nsteps=1, sort_interval=0, energies=False):
         en = np.zeros((nsteps, 2)) if energies else None

@@ -85,6 +85,7 @@ struct CtxBase {
     virtual int advance_e(double px, double py, double pz, double dt_eps0) = 0;
     virtual int uncenter(double qdt_2mc) = 0;
     virtual int energies_async(double* dev_out2) = 0;
+    virtual int kinetic_async(double* dev_out) = 0;
     virtual int update_ghosts(int which) = 0;
     virtual int sort() = 0;
     virtual int push_reorder(const cpic_consts& k) = 0;
@@ -555,6 +556,14 @@ struct Ctx final : CtxBase {
         if (nb > 148 * 8) nb = 148 * 8;
         k_energy<R><<<nb, 256, 0, stream>>>(F(), g, b, em ? 1 : 0, dev_out2);
         return check_launch("k_energy");
+    }
+    int kinetic_async(double* dev_out) override {
+        cudaMemsetAsync(dev_out, 0, sizeof(double), stream);
+        if (np == 0) return CPIC_OK;
+        unsigned nb = blocks_for(np);
+        if (nb > 148 * 8) nb = 148 * 8;
+        k_kinetic_energy<R><<<nb, 256, 0, stream>>>(P[cur], np, dev_out);
+        return check_launch("k_kinetic_energy");
     }
     double* energy_scratch() override { return en_dev; }
     unsigned long long* stats_dev() override { return stats; }
@@ -1066,6 +1075,19 @@ int cpic_energies(cpic_ctx* ctx, double* e_energy, double* b_energy) {
     // reference: e_tot*0.5f*dV with dV = 1 (src/fields.h:584-585); B energy is 0 for ES
     if (e_energy) *e_energy = 0.5 * h[0];
     if (b_energy) *b_energy = (c->prm.solver == CPIC_SOLVER_EM) ? 0.5 * h[1] : 0.0;
+    return CPIC_OK;
+}
+
+int cpic_kinetic_energy(cpic_ctx* ctx, double* out) {
+    CTX_HOSTNP(ctx);
+    if (!out) return c->fail(CPIC_E_INVALID, "kinetic_energy: null");
+    double* d = c->energy_scratch();
+    int rc = c->kinetic_async(d);
+    if (rc) return rc;
+    double h = 0.0;
+    if ((rc = c->cuda(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream), "D2H kinetic energy"))) return rc;
+    if ((rc = c->cuda(cudaStreamSynchronize(c->stream), "kinetic_energy"))) return rc;
+    *out = h;
     return CPIC_OK;
 }
 

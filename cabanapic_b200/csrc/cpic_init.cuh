@@ -71,4 +71,26 @@ __global__ void __launch_bounds__(256) k_init_uniform_plasma(Particles<R> p, Uni
     p.rec[n] = r;
 }
 
+// Kinetic energy diagnostic (absent upstream): out[0] += sum_p w_p (gamma_p - 1), gamma = sqrt(1 + u.u),
+// evaluated as u.u / (gamma + 1) in double (no cancellation for cold particles); block tree + one atomic per block.
+template <class R>
+__global__ void __launch_bounds__(256) k_kinetic_energy(Particles<R> p, long long np, double* __restrict__ out) {
+    double e = 0.0;
+    for (long long n = blockIdx.x * 256LL + threadIdx.x; n < np; n += (long long)gridDim.x * 256) {
+        const PHalf<R> m = p.rec[n].mom;
+        const double u2 = (double)m.x * m.x + (double)m.y * m.y + (double)m.z * m.z;
+        e += (double)m.w * (u2 / (sqrt(1.0 + u2) + 1.0));
+    }
+    __shared__ double se[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) se[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += se[k];
+        atomicAdd(out, t);
+    }
+}
+
 }  // namespace cpic

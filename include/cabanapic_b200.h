@@ -131,6 +131,11 @@ int  cpic_advance_b(cpic_ctx* ctx, double px, double py, double pz);     /* src/
 int  cpic_advance_e(cpic_ctx* ctx, double px, double py, double pz, double dt_eps0); /* src/fields.h:365-378, 618-665, 511-544 */
 int  cpic_uncenter_particles(cpic_ctx* ctx, double qdt_2mc);      /* src/uncenter_p.h:4-105       */
 int  cpic_energies(cpic_ctx* ctx, double* e_energy, double* b_energy);   /* src/fields.h:556-615, 484-509 */
+/* Kinetic energy of the particles, sum_p w_p (gamma_p - 1) with gamma = sqrt(1 + u.u), accumulated in double
+ * (in units of m c^2 per unit weight).  The reference has no such diagnostic; together with
+ * cpic_energies it closes the energy budget: w_p (gamma-1) m c^2 + (eps0/2) sum (E^2 + cB^2) dV is conserved by
+ * the scheme up to grid heating, a size-independent check of the whole loop. */
+int  cpic_kinetic_energy(cpic_ctx* ctx, double* out);
 int  cpic_update_ghosts(cpic_ctx* ctx, int which /* 0: fold J, 1: copy J, 2: copy cB, 3 / 4: first / second sweep of the J fold only */); /* src/fields.h:11-271 */
 
 /* n whole steps in the reference's order (example/example.cpp:221-266), fused on the

@@ -391,6 +391,50 @@ def test_current_conservation_at_scale():
     assert np.abs(p1["dx"]).max() <= 1 and np.abs(p1["dy"]).max() <= 1 and np.abs(p1["dz"]).max() <= 1
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_kinetic_energy_diagnostic(prec):
+    """cpic_kinetic_energy (sum w (gamma - 1), double accumulation; the reference has no such diagnostic,
+    SURVEY 8f.1) against numpy in float64 on a random state incl. cold and relativistic particles."""
+    s = random_state(6, 5, 4, nppc=50, prec=prec, seed=17)
+    s.p["ux"][:10] = 0; s.p["uy"][:10] = 0; s.p["uz"][:10] = 1e-6      # cold: gamma - 1 ~ 5e-13
+    s.p["ux"][10:20] = 30.0                                              # relativistic
+    with make_ctx(s) as c:
+        got = c.kinetic_energy()
+    u2 = sum(s.p[n].astype(np.float64) ** 2 for n in ("ux", "uy", "uz"))
+    want = float(np.sum(s.p["w"].astype(np.float64) * (u2 / (np.sqrt(1.0 + u2) + 1.0))))
+    assert abs(got - want) <= 1e-12 * want
+
+
+def test_energy_budget_is_conserved_at_scale():
+    """Size-independent property of the whole loop (push + deposit + field advance) on the bench plasma at 64^3
+    cells x 16 ppc = 4.2 M particles, 60 reordering steps: kinetic energy sum w (gamma-1) m c^2 plus field energy
+    (eps0/2) sum (E^2 + cB^2) dV stays constant while the fields grow out of the deposit noise at the particles'
+    expense.  Observed drift 4e-5 of the kinetic energy (explicit-PIC grid heating at dx = lambda_D); bar 5e-4."""
+    m = cp()
+    from cabanapic_b200 import decks
+    d = decks.uniform_plasma(64, 64, 64, 16)
+    k, _, we = d.consts()
+    n = d.num_particles
+    dV = k.dx * k.dy * k.dz
+    with m.Context(64, 64, 64, 1, max_particles=n, real=np.float32) as c:
+        c.init_uniform_plasma(0, n, 64, 64, 64, 16, weight=we)
+        c.upload_fields(d.initial_fields())
+        ke0 = c.kinetic_energy()
+        e0, b0 = c.energies()
+        assert e0 == 0.0 and b0 == 0.0
+        tot = []
+        for _ in range(6):
+            c.step(k, 10, m.SORT_FUSED, False)
+            e, b = c.energies()
+            tot.append((c.kinetic_energy(), (e + b) * dV))
+        ke1, fe1 = tot[-1]
+        print(f"KE0 {ke0:.6e}  KE {ke1:.6e}  field {fe1:.6e}  drift {(ke1 + fe1 - ke0) / ke0:.3e}")
+        assert fe1 > 0 and fe1 < 0.05 * ke0
+        assert ke1 < ke0                                           # the particles paid for the fields
+        for ke, fe in tot:
+            assert abs(ke + fe - ke0) <= 5e-4 * ke0
+
+
 def test_full_size_c5_properties():
     """BASELINE configs[4] at FULL size (256^3 cells x 64 ppc = 2^30 particles, 69 GB of particle store) through
     size-independent properties, all evaluated on the device.  The weights are first made a tag (2^20 classes of
