@@ -100,6 +100,7 @@ struct CtxBase {
     virtual int slab_append_async(const void* buf, long long cap, const long long* count_dev) = 0;
     virtual bool few_cells() const = 0;   // grid small enough for the block-private accumulator (k_push2<PRIV>)
     virtual int sync_np() = 0;      // device-count mode -> host-count mode (synchronises); no-op otherwise
+    bool skip_dense = false;        // PUSH2_PLACE builds: cpic_step(FUSED) keeps the store in segment form between calls
     long long fb_steps = 0;         // steps taken in the few-cells fallback of CPIC_SORT_FUSED (sort when % 8 == 0)
     bool dev_count = false;         // slab mode: np lives in dc[0] on the device, the host's np is stale
     virtual int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
@@ -142,6 +143,9 @@ struct Ctx final : CtxBase {
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer); cudaFree(fields); cudaFree(interp); cudaFree(acc);
             cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count); cudaFree(dc);
+#if PUSH2_PLACE
+            cudaFree(seg_start); cudaFree(over_count); cudaFree(place_info);
+#endif
             for (auto b : hs_buf) cudaFree(b);
             for (auto e : hs_ev) if (e) cudaEventDestroy(e);
             if (hs_up) cudaStreamDestroy(hs_up);
@@ -192,11 +196,11 @@ struct Ctx final : CtxBase {
         if ((rc = cuda(cudaMalloc(&en_dev, 2 * sizeof(double)), "cudaMalloc"))) return rc;
         if ((rc = cuda(cudaMalloc(&stats, 8 * sizeof(unsigned long long)), "cudaMalloc"))) return rc;
         if (prm.enable_sort) {
-            n_l1 = (g.nc + SCAN_TILE - 1) / SCAN_TILE;
+            n_l1 = (g.nc + 1 + SCAN_TILE - 1) / SCAN_TILE;       // (+1: the placing push scans a sentinel entry as well)
             n_l2 = (n_l1 + SCAN_TILE - 1) / SCAN_TILE;
             if (n_l2 > SCAN_TILE) return fail(CPIC_E_INVALID, "grid too large for the 3-level cell scan");
-            if ((rc = cuda(cudaMalloc(&cell_count, (size_t)g.nc * sizeof(unsigned)), "cudaMalloc(cell_count)"))) return rc;
-            if ((rc = cuda(cudaMalloc(&cell_count2, (size_t)g.nc * sizeof(unsigned)), "cudaMalloc(cell_count2)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&cell_count, (size_t)(g.nc + 1) * sizeof(unsigned)), "cudaMalloc(cell_count)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&cell_count2, (size_t)(g.nc + 1) * sizeof(unsigned)), "cudaMalloc(cell_count2)"))) return rc;
             if ((rc = cuda(cudaMalloc(&scan_l1, (size_t)n_l1 * sizeof(unsigned)), "cudaMalloc"))) return rc;
             if ((rc = cuda(cudaMalloc(&scan_l2, (size_t)n_l2 * sizeof(unsigned)), "cudaMalloc"))) return rc;
         }
@@ -440,6 +444,9 @@ struct Ctx final : CtxBase {
         return CPIC_OK;
     }
     int sync_np() override {
+#if PUSH2_PLACE
+        { int rcd = make_dense(); if (rcd) return rcd; }
+#endif
         if (!dev_count) return CPIC_OK;
         long long h[4] = {0, 0, 0, 0};
         int rc;
@@ -634,12 +641,99 @@ struct Ctx final : CtxBase {
     // The reordering push (cpic_push2.cuh, REORD): cpic_push + the cell ordering of the particle store in one
     // pass.  prepare_reorder() makes cell_count the exclusive scan of the current cells' histogram (from the
     // previous reordering push when there was one); push_reorder() consumes it.
+#if PUSH2_PLACE
+    // ---- experimental placement by the NEW cell (cpic_push2.cuh, PUSH2_PLACE)
+    unsigned* seg_start = nullptr;      // nc + 1: immutable segment starts of the push in flight
+    unsigned* over_count = nullptr;
+    long long* place_info = nullptr;    // [0] extent of the store (segments + tail) [1] error flags
+    bool placed = false;                // P[cur] has segment form: holes (cell -1) and an overflow tail
+    bool place_ok() const {
+        return can_reorder() && !use_priv() && (g.per & 4) && prm.boundary == CPIC_BOUNDARY_PERIODIC && !dev_count && !want_stats &&
+               cap >= np + g.nc + np / 12 + 4096;
+    }
+    int push_place(const cpic_consts& k) {
+        int rc;
+        if (!seg_start) {
+            if ((rc = cuda(cudaMalloc(&seg_start, (size_t)(g.nc + 1) * sizeof(unsigned)), "cudaMalloc(seg_start)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&over_count, sizeof(unsigned)), "cudaMalloc"))) return rc;
+            if ((rc = cuda(cudaMalloc(&place_info, 2 * sizeof(long long)), "cudaMalloc"))) return rc;
+            cudaMemsetAsync(place_info, 0, 2 * sizeof(long long), stream);
+        }
+        // capacities (counts rounded up to even) -> segment starts; cell_count becomes the mutable cursor
+        if (!hist_valid) {          // only possible on a dense store (a placing push always leaves the histogram)
+            cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
+            cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
+            k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
+            if ((rc = check_launch("k_cell_histogram"))) return rc;
+        }
+        hist_valid = false; cursor_valid = false;
+        k_even_caps<<<blocks_for(g.nc + 1), 256, 0, stream>>>(cell_count, g.nc);
+        if ((rc = check_launch("k_even_caps"))) return rc;
+        if ((rc = scan_cells(g.nc + 1))) return rc;
+        cudaMemcpyAsync(seg_start, cell_count, (size_t)(g.nc + 1) * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream);
+        cudaMemsetAsync(over_count, 0, sizeof(unsigned), stream);
+        if constexpr (std::is_same<R, float>::value) {
+            PushArgs<float> a = push_args(k);
+            a.leave_list = nullptr;
+            a.dst = P[cur ^ 1];
+            a.cursor = cell_count;
+            a.hist = cell_count2;
+            a.seg_start = seg_start; a.over = over_count; a.ncells = (int)g.nc; a.dst_cap = (unsigned)cap;
+            if (placed) { a.np_dev = place_info; a.np = cap; }
+            cudaMemsetAsync(cell_count2, 0, (size_t)g.nc * sizeof(unsigned), stream);
+            cudaEventRecord(ev[0], stream);
+            const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
+            const float aq = fabsf((float)a.qdt_2mc);
+            const bool fd = push2_fastds && (aq == 0.f || (aq > 1e-12f && aq < 1e12f));
+            if (fd) rc = fma ? launch_push2h<true, false, true, true, true>(a) : launch_push2h<false, false, true, true, true>(a);
+            else rc = fma ? launch_push2h<true, false, false, true, true>(a) : launch_push2h<false, false, false, true, true>(a);
+            cudaEventRecord(ev[1], stream);
+            ev_valid[0] = true;
+            if (rc) return rc;
+            k_place_finish<R><<<blocks_for(g.nc), 256, 0, stream>>>(P[cur ^ 1], cell_count, seg_start, g.nc, over_count, cap, place_info);
+            if ((rc = check_launch("k_place_finish"))) return rc;
+            if (getenv("CPIC_PLACE_DEBUG")) {
+                long long h[2]; unsigned ov = 0, t = 0;
+                cudaStreamSynchronize(stream);
+                cudaMemcpy(h, place_info, sizeof h, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&ov, over_count, sizeof ov, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&t, seg_start + g.nc, sizeof t, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[place] np %lld  segments %u  tail slots %u  extent %lld  err %lld\n", np, t, ov, h[0], h[1]);
+            }
+            cur ^= 1;
+            std::swap(cell_count, cell_count2);
+            hist_valid = true;
+            placed = true;
+            want_hist = false;
+        }
+        return CPIC_OK;
+    }
+    // segment form -> dense, cell-ordered store (everything but the placing push expects that)
+    int make_dense() {
+        if (!placed || skip_dense) return CPIC_OK;
+        int rc;
+        // cell_count = histogram of the current cells (left by the placing push) -> offsets -> scatter the valid records
+        if ((rc = scan_cells())) return rc;
+        k_sort_scatter_ext<R><<<148 * 16, 256, 0, stream>>>(P[cur], P[cur ^ 1], place_info, cell_count);
+        if ((rc = check_launch("k_sort_scatter_ext"))) return rc;
+        cur ^= 1;
+        placed = false; hist_valid = false; cursor_valid = false; leavers_valid = false;
+        long long h[2] = {0, 0};
+        if ((rc = cuda(cudaMemcpyAsync(h, place_info, sizeof h, cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(stream), "make_dense"))) return rc;
+        if (h[1]) { cudaMemsetAsync(place_info, 0, 2 * sizeof(long long), stream); return fail(CPIC_E_CAPACITY, "push_reorder: the overflow tail of the placing push exceeded the store capacity %lld", cap); }
+        return CPIC_OK;
+    }
+#endif
     bool can_reorder() const {
         const int dep = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
         return std::is_same<R, float>::value && use_push2 && prm.enable_sort && dep == CPIC_DEPOSIT_WARP;
     }
     int prepare_reorder() override {
         if (!prm.enable_sort) return fail(CPIC_E_INVALID, "push_reorder: context was created with enable_sort=0");
+#if PUSH2_PLACE
+        if (!use_priv()) return CPIC_OK;
+#endif
         if (np == 0 || cursor_valid) return CPIC_OK;
         int rc;
         if (!hist_valid) {
@@ -660,6 +754,14 @@ struct Ctx final : CtxBase {
         }
         if (np == 0) return CPIC_OK;
         int rc;
+#if PUSH2_PLACE
+        if (place_ok()) return push_place(k);
+        if (!use_priv()) {          // (this build's REORD kernels place by new cell: no old-style reordering push to fall back to)
+            if ((rc = make_dense())) return rc;
+            rc = sort();
+            return rc ? rc : push(k);
+        }
+#endif
         if ((rc = prepare_reorder())) return rc;
         if constexpr (std::is_same<R, float>::value) {
             PushArgs<float> a = push_args(k);
@@ -701,6 +803,7 @@ struct Ctx final : CtxBase {
         a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         a.np_dev = nullptr;
+        a.seg_start = nullptr; a.over = nullptr; a.ncells = 0; a.dst_cap = 0;
         a.priv_nc = use_priv() ? (int)g.nc : 0;
         a.ko = 0;
 #ifdef PUSH2_KO_RT
@@ -712,6 +815,7 @@ struct Ctx final : CtxBase {
         if (np == 0) return CPIC_OK;
         PushArgs<R> a;
         a.ko = 0; a.np_dev = nullptr; a.priv_nc = use_priv() ? (int)g.nc : 0;
+        a.seg_start = nullptr; a.over = nullptr; a.ncells = 0; a.dst_cap = 0;
         a.dst = P[cur]; a.cursor = nullptr;
         a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
         a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
@@ -864,9 +968,11 @@ struct Ctx final : CtxBase {
         return check_launch("k_uncenter");
     }
 
-    int scan_cells() {
-        // exclusive scan of cell_count in place (3 levels of 2048-wide tiles)
-        k_scan_tile<<<(unsigned)n_l1, 256, 0, stream>>>(cell_count, cell_count, g.nc, scan_l1);
+    int scan_cells(long long n = -1) {
+        // exclusive scan of cell_count[0, n) in place (3 levels of 2048-wide tiles); n = nc, or nc + 1 (placing push)
+        if (n < 0) n = g.nc;
+        const long long n_l1 = (n + SCAN_TILE - 1) / SCAN_TILE, n_l2 = (n_l1 + SCAN_TILE - 1) / SCAN_TILE;
+        k_scan_tile<<<(unsigned)n_l1, 256, 0, stream>>>(cell_count, cell_count, n, scan_l1);
         int rc = check_launch("k_scan_tile");
         if (rc) return rc;
         if (n_l1 > 1) {
@@ -878,7 +984,7 @@ struct Ctx final : CtxBase {
                 k_scan_add<<<(unsigned)n_l2, 256, 0, stream>>>(scan_l1, n_l1, scan_l2);
                 if ((rc = check_launch("k_scan_add"))) return rc;
             }
-            k_scan_add<<<(unsigned)n_l1, 256, 0, stream>>>(cell_count, g.nc, scan_l1);
+            k_scan_add<<<(unsigned)n_l1, 256, 0, stream>>>(cell_count, n, scan_l1);
             if ((rc = check_launch("k_scan_add"))) return rc;
         }
         return CPIC_OK;
@@ -1092,7 +1198,9 @@ int cpic_kinetic_energy(cpic_ctx* ctx, double* out) {
 }
 
 int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, double* energies) {
-    CTX_HOSTNP(ctx);
+    CTX_OR_FAIL(ctx);
+    c->skip_dense = sort_interval == CPIC_SORT_FUSED;
+    { const int rc_np_ = c->sync_np(); c->skip_dense = false; if (rc_np_) return rc_np_; }
     if (!k || nsteps < 0 || sort_interval < CPIC_SORT_FUSED) return c->fail(CPIC_E_INVALID, "step: bad arguments");
     int rc = CPIC_OK;
     double* en = nullptr;
