@@ -147,6 +147,13 @@ def cpu_reference_run(grid_xy, nppc, steps, warmup, min_seconds=0.0, max_steps=N
         s.p[n][:] = p[n]
     sample = f"{nx}x{ny}x{nz} cells x {nppc} ppc = {d.num_particles} particles of the same plasma, float, EM"
     if RefLib.available("default", "f32", omp=True):
+        # all the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+        # silently turn the reference arm into a single-thread run
+        try:
+            import ctypes
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(len(os.sched_getaffinity(0)))
+        except Exception:
+            pass
         R = RefLib("default", "f32", omp=True).create(s, solver=0)
         cores, kind = R.num_threads(), "reference"
         run = lambda n: R.run(ok, n)
