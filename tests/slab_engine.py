@@ -8,7 +8,10 @@ from oracle.api import PARTICLE_NAMES, Consts as OConsts, Restatement, State
 
 
 class OracleEngine:
-    def __init__(self, nx, ny, nz, capacity, prec="f32", z_periodic=True):
+    def __init__(self, nx, ny, nz, capacity, prec="f32", z_periodic=True, async_migration=False):
+        # async_migration: offer the device-counted migration interface of GpuEngine (counts travel as tensors, the
+        # stepper never sees them as Python ints) so that its exchange choreography runs under gloo too
+        self.async_migration = async_migration
         self.nx, self.ny, self.nz = nx, ny, nz
         self.prec = prec
         self.real = np.dtype(np.float32 if prec == "f32" else np.float64)
@@ -77,6 +80,14 @@ class OracleEngine:
             self.s.p[k][:len(keep)] = self.s.p[k][keep]
         self.s.np = len(keep)
         return tuple(out)
+
+    def extract_async(self, lo, hi, cap, counts, rebase_lo, rebase_hi):
+        n_lo, n_hi = self.extract_z_leavers(lo, hi, cap, rebase_lo, rebase_hi)
+        counts[0] = n_lo
+        counts[1] = n_hi
+
+    def append_async(self, buf, cap, count):
+        self.append(buf, cap, int(count[0]))
 
     def append(self, buf, cap, n):
         if n == 0:

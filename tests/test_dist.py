@@ -56,7 +56,7 @@ def _split_state(s, z0, nzl):
     return lf, p, np.nonzero(sel)[0]
 
 
-def _slab_worker(rank, world, port, prec, grid, nsteps, outdir):
+def _slab_worker(rank, world, port, prec, grid, nsteps, outdir, use_async=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -70,16 +70,17 @@ def _slab_worker(rank, world, port, prec, grid, nsteps, outdir):
         ranges = slab_ranges(nz, world)
         z0, nzl = ranges[rank]
         lf, p, _ = _split_state(s, z0, nzl)
-        e = OracleEngine(nx, ny, nzl, capacity=3 * len(p["cell"]) + 64, prec=prec, z_periodic=False)
+        e = OracleEngine(nx, ny, nzl, capacity=3 * len(p["cell"]) + 64, prec=prec, z_periodic=False, async_migration=use_async)
         e.s.f[:] = lf
         e.set_particles(p)
         st = SlabStepper(e, Consts(**k.to_dict()), rank, world, ranges[(rank - 1) % world][1],
                          ranges[(rank + 1) % world][1], send_capacity=len(p["cell"]) + 16)
         mig, en = [], []
         for _ in range(nsteps):
-            st.step()
+            st.step(fused=use_async)       # the device-counted exchange is what fused steps use when the engine has it
             mig.append(st.last_migration)
             en.append(st.energies())
+        assert st._async_used == use_async if use_async else True
         out = e.particles()
         out["cell"] = out["cell"] + z0 * (nx + 2) * (ny + 2)       # back to global numbering
         np.savez(os.path.join(outdir, f"slab_{rank}.npz"), f=e.s.f, mig=np.array(mig), en=np.array(en),
@@ -88,11 +89,14 @@ def _slab_worker(rank, world, port, prec, grid, nsteps, outdir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("use_async", [False, True])
 @pytest.mark.parametrize("prec,tol", [("f64", 1e-12), ("f32", 2e-5)])
-def test_slab_mode_matches_single_domain_oracle(tmp_path, prec, tol):
+def test_slab_mode_matches_single_domain_oracle(tmp_path, prec, tol, use_async):
+    """use_async: the one-batch exchange with the counts travelling as tensors (accumulator planes + counts +
+    whole capacity-sized particle payloads in ONE group of sends/receives), as the GPU runs use it."""
     world, grid, nsteps = 2, (5, 4, 6), 6
     nx, ny, nz = grid
-    mp.spawn(_slab_worker, args=(world, _free_port(), prec, grid, nsteps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_slab_worker, args=(world, _free_port(), prec, grid, nsteps, str(tmp_path), use_async), nprocs=world, join=True)
     # single-domain oracle on the same state, tracking per-step slab crossings
     s = random_state(nx, ny, nz, nppc=12, prec=prec, seed=21)
     k = consts_for(nx, ny, nz, prec)
