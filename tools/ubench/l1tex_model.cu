@@ -1,4 +1,4 @@
-// Micro-benchmark (written at the end of round 1, NOT yet run -- no GPU minutes were left): what does ONE warp-wide memory
+// Micro-benchmark (end of round 1; results: profiles/r03_ubench_l1tex_model.log): what does ONE warp-wide memory
 // instruction of each kind used by k_push2 cost the SM, as a function of how many distinct 128-byte lines its 32 lanes
 // touch?  The kernel's knock-outs add up linearly and neither occupancy nor an L1-resident gather moves the total
 // (DESIGN.md 9.1), while the busiest unit ncu reports is the L1TEX data pipe at 70 % -- this measures the cost model
@@ -9,6 +9,7 @@
 //               optionally (bit 8 of the pattern) with pattern-1 reductions in flight from the same warp
 //    pattern 3  STG.256 (whole record)       D distinct lines (D = 8: a contiguous 1 KB tile)
 //    pattern 4  LDS.128 / STS.128 pair, conflict-free (the deposit rows)
+//    pattern 5  LDG.256 (whole record)       6  the record store as two STG.128
 // Persistent grid of 148 x 3 blocks x 8 warps like k_push2; every warp issues ITER instructions of the pattern on
 // addresses that change per iteration (hash), all inside a table that fits L2 (default 32 MB).  Output: ns per
 // warp-instruction per SM (= SM-cycles at the measured clock) for D = 1, 2, 4, 8, 16, 32.
@@ -56,6 +57,15 @@ __global__ void __launch_bounds__(256, 3) k_model(char* table, size_t nlines, in
             // D lines: D = 8 -> one contiguous KB; larger D -> every record in its own line
             const size_t line = hash32(it * 64u + (D <= 8 ? 0 : lane) + salt) % (nlines - 8);
             *reinterpret_cast<Rec*>(table + line * 128 + (D <= 8 ? (size_t)lane * 32 : 0)) = r;
+        } else if (PATTERN == 5) {            // LDG.256: the record load (D <= 8: a contiguous KB, else one line per record)
+            const size_t line = hash32(it * 64u + (D <= 8 ? 0 : lane) + salt) % (nlines - 8);
+            const Rec r = *reinterpret_cast<const Rec*>(table + line * 128 + (D <= 8 ? (size_t)lane * 32 : 0));
+            keep += r.v[0] + r.v[7];
+        } else if (PATTERN == 6) {            // the same record store as two STG.128
+            const size_t line = hash32(it * 64u + (D <= 8 ? 0 : lane) + salt) % (nlines - 8);
+            float4* q = reinterpret_cast<float4*>(table + line * 128 + (D <= 8 ? (size_t)lane * 32 : 0));
+            q[0] = make_float4(keep, 1.f, 2.f, 3.f);
+            q[1] = make_float4(keep, 5.f, 6.f, 7.f);
         } else {
             rows[warp][lane * 3 + 0] = make_float4(keep, 1.f, 2.f, 3.f);
             __syncwarp();
@@ -106,6 +116,8 @@ int main(int argc, char** argv) {
     run<2 + 256>("ATOMG.ADD.U32 + immediate use, REDs in flight", table, nlines, iters, sink, ghz);
     run<3>("STG.256 record store (D<=8: contiguous KB)", table, nlines, iters, sink, ghz);
     run<4>("STS.128 + LDS.128 + 2 syncwarp", table, nlines, iters, sink, ghz);
+    run<5>("LDG.256 record load (D<=8: contiguous KB)", table, nlines, iters, sink, ghz);
+    run<6>("2 x STG.128 record store (D<=8: contiguous KB)", table, nlines, iters, sink, ghz);
     printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
