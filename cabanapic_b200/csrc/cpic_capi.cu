@@ -18,6 +18,7 @@
 #include "cpic_fields.cuh"
 #include "cpic_particles.cuh"
 #include "cpic_push2.cuh"
+#include "cpic_push3.cuh"
 #include "cpic_sort.cuh"
 #include "cpic_init.cuh"
 #include "cpic_migrate.cuh"
@@ -42,6 +43,8 @@ struct CtxBase {
     bool want_hist = false;    // set by cpic_step before a push that is followed by a sort
     bool hist_valid = false;   // cell_count holds the histogram of the current cells (from the last push)
     bool cursor_valid = false; // cell_count holds the exclusive scan of that histogram (ready for a reordering push)
+    bool seg_valid = false;    // the store is the concatenation of the per-cell segments seg[seg_cur] (k_push3), up to the
+                               // hole filling / appended tail of a slab migration
     bool leavers_valid = false; // slab mode: the last push listed the particles it left in the z ghost planes
     bool ghost_clean = false;   // no particle sits in a z ghost plane (true after init_uniform_plasma or an extraction;
                                 // unknown after an upload): only then does the mover's list find every leaver
@@ -142,7 +145,7 @@ struct Ctx final : CtxBase {
             cudaSetDevice(prm.device);
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer); cudaFree(fields); cudaFree(interp); cudaFree(acc);
-            cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count); cudaFree(dc);
+            cudaFree(seg[0]); cudaFree(seg[1]); cudaFree(cursor3); cudaFree(work3); cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count); cudaFree(dc);
 #if PUSH2_PLACE
             cudaFree(seg_start); cudaFree(over_count); cudaFree(place_info);
 #endif
@@ -206,6 +209,7 @@ struct Ctx final : CtxBase {
         }
         // Field_Solver ctor zeroes the fields (src/fields.h:279-315); interpolators are zeroed by
         // initialize_interpolator (src/interpolator.cpp:125-172); Kokkos::View zero-initialises.
+        if ((rc = init_push3())) return rc;
         cudaMemsetAsync(fields, 0, (size_t)nc_pad * F_N * sizeof(R), stream);
         cudaMemsetAsync(interp, 0, (size_t)g.nc * S * sizeof(R), stream);
         cudaMemsetAsync(acc, 0, (size_t)g.nc * 12 * sizeof(R), stream);
@@ -229,7 +233,7 @@ struct Ctx final : CtxBase {
             if ((rc = check_launch("k_pack_records"))) return rc;
         }
         np = n;
-        hist_valid = false; cursor_valid = false; leavers_valid = false; ghost_clean = false;
+        hist_valid = false; cursor_valid = false; seg_valid = false; leavers_valid = false; ghost_clean = false;
         // bounds-check the cell indices once on upload (would have caught decks/2stream-short.cxx)
         if (n > 0) {
             k_check_cells<R><<<blocks_for(n), 256, 0, stream>>>(P[cur], n, g.nc, bad);
@@ -725,12 +729,134 @@ struct Ctx final : CtxBase {
         return CPIC_OK;
     }
 #endif
+    // ---- block-owned reordering push (cpic_push3.cuh): chunks of cells per CTA, TMA-staged interpolators
+    unsigned* seg[2] = {nullptr, nullptr};   // exclusive scans (nc + 1 entries + pad): segment bounds of the store, ping-pong
+    unsigned* cursor3 = nullptr;             // the mutable copy of the destination bounds the push claims slots from
+    unsigned* work3 = nullptr;               // dynamic work counter
+    int seg_cur = 0;                         // seg[seg_cur] describes P[cur] while seg_valid
+    bool use_push3 = true;
+    int p3_ch = 0, p3_cpp = 0, p3_yblock = 16;
+    bool push3_ok() const { return use_push3 && can_reorder() && !use_priv() && seg[0] != nullptr; }
+    int init_push3() {
+        int rc;
+        if (const char* e = getenv("CPIC_PUSH3")) use_push3 = atoi(e) != 0;
+        if (const char* e = getenv("CPIC_PUSH3_YBLOCK")) p3_yblock = std::max(1, atoi(e));
+        if (!std::is_same<R, float>::value || !prm.enable_sort) return CPIC_OK;
+        for (auto& b : seg)
+            if ((rc = cuda(cudaMalloc(&b, (size_t)(g.nc + 16) * sizeof(unsigned)), "cudaMalloc(segment bounds)"))) return rc;
+        if ((rc = cuda(cudaMalloc(&cursor3, (size_t)(g.nc + 16) * sizeof(unsigned)), "cudaMalloc(cursor)"))) return rc;
+        if ((rc = cuda(cudaMalloc(&work3, sizeof(unsigned)), "cudaMalloc"))) return rc;
+        // chunk = whole x-rows while they fit (and while there are enough chunks to balance the CTAs), else a piece of a row
+        const int plane = g.gx * g.gy;
+        int ch = PUSH3_CH_MAX;
+        if (g.gx <= PUSH3_CH_MAX) {
+            int rows = PUSH3_CH_MAX / g.gx;
+            while (rows > 1 && (long long)((g.gy + rows - 1) / rows) * g.gz < 16ll * 148 * PUSH3_MIN_BLOCKS) --rows;
+            ch = rows * g.gx;
+        }
+        if (const char* e = getenv("CPIC_PUSH3_CH")) ch = std::min(PUSH3_CH_MAX, std::max(4, atoi(e)));
+        p3_ch = std::min(ch, plane);
+        p3_cpp = (plane + p3_ch - 1) / p3_ch;
+        return CPIC_OK;
+    }
+    // exclusive scan of the current cells' histogram (cell_count, left intact) into dstbuf[0 .. nc]; dstbuf[nc] = total
+    int scan_hist_into(unsigned* dstbuf) {
+        int rc;
+        if ((rc = cuda(cudaMemcpyAsync(dstbuf, cell_count, (size_t)g.nc * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream), "D2D histogram"))) return rc;
+        cudaMemsetAsync(dstbuf + g.nc, 0, 16 * sizeof(unsigned), stream);
+        return scan_buf(dstbuf, g.nc + 1);
+    }
+    // bring the store into segment form: counting sort by cell, keeping the bounds (seg) and the histogram (cell_count)
+    int establish_segments() {
+        int rc;
+        if (!hist_valid) {
+            cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
+            cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
+            k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
+            if ((rc = check_launch("k_cell_histogram"))) return rc;
+            hist_valid = true;
+        }
+        cudaEventRecord(ev[2], stream);
+        if ((rc = scan_hist_into(seg[seg_cur]))) return rc;
+        if ((rc = cuda(cudaMemcpyAsync(cursor3, seg[seg_cur], (size_t)g.nc * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream), "D2D cursor"))) return rc;
+        k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cursor3);
+        if ((rc = check_launch("k_sort_scatter"))) return rc;
+        cur ^= 1;
+        cudaEventRecord(ev[3], stream);
+        ev_valid[1] = true;
+        cursor_valid = false; leavers_valid = false;
+        seg_valid = true;
+        return CPIC_OK;
+    }
+    template <bool FMA, bool ST, bool FD>
+    int launch_push3(const Push3Args& q) {
+        auto kern = k_push3<FMA, ST, FD>;
+        const size_t smem = sizeof(Push3Smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PUSH3_WARPS * 32, smem);
+        if (per_sm < 1) per_sm = 1;
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, prm.device);
+        long long blocks = (long long)sms * per_sm;
+        if (push_grid > 0) blocks = push_grid;
+        volatile float one = 1.0f;     // a runtime value as far as the compiler is concerned (cpic_push2.cuh)
+        kern<<<(unsigned)blocks, PUSH3_WARPS * 32, smem, stream>>>(q, one);
+        return check_launch("k_push3");
+    }
+    int push_reorder3(const cpic_consts& k) {
+        int rc;
+        if (!seg_valid) {
+            if (dev_count && (rc = sync_np())) return rc;
+            if (np == 0) return CPIC_OK;
+            if ((rc = establish_segments())) return rc;
+        }
+        if constexpr (std::is_same<R, float>::value) {
+            const int so = seg_cur ^ 1;
+            // destination bounds = scan of the histogram of the cells the particles are in now
+            if ((rc = scan_hist_into(seg[so]))) return rc;
+            if ((rc = cuda(cudaMemcpyAsync(cursor3, seg[so], (size_t)g.nc * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream), "D2D cursor"))) return rc;
+            cudaMemsetAsync(cell_count2, 0, (size_t)g.nc * sizeof(unsigned), stream);
+            cudaMemsetAsync(work3, 0, sizeof(unsigned), stream);
+            Push3Args q;
+            q.a = push_args(k);
+            if ((rc = arm_leave_list(q.a))) return rc;
+            q.a.dst = P[cur ^ 1];
+            q.a.cursor = cursor3;
+            q.a.hist = cell_count2;
+            q.a.priv_nc = 0;
+            if (dev_count) { q.a.np_dev = dc; q.a.np = cap; }
+            q.sin = seg[seg_cur];
+            q.ch = p3_ch; q.cpp = p3_cpp; q.gz = g.gz; q.plane = g.gx * g.gy; q.yblock = p3_yblock;
+            q.nchunks = p3_cpp * g.gz; q.nc = (int)g.nc;
+            q.work = work3;
+            if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
+            cudaEventRecord(ev[0], stream);
+            const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
+            const float aq = fabsf((float)q.a.qdt_2mc);
+            const bool fd = push2_fastds && (aq == 0.f || (aq > 1e-12f && aq < 1e12f));
+            if (want_stats) rc = fma ? launch_push3<true, true, false>(q) : launch_push3<false, true, false>(q);
+            else if (fd) rc = fma ? launch_push3<true, false, true>(q) : launch_push3<false, false, true>(q);
+            else rc = fma ? launch_push3<true, false, false>(q) : launch_push3<false, false, false>(q);
+            cudaEventRecord(ev[1], stream);
+            ev_valid[0] = true;
+            if (rc) return rc;
+            cur ^= 1;
+            seg_cur = so;
+            std::swap(cell_count, cell_count2);      // cell_count: histogram of the cells the particles are in now
+            hist_valid = true;
+            cursor_valid = false;
+            want_hist = false;
+        }
+        return CPIC_OK;
+    }
     bool can_reorder() const {
         const int dep = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
         return std::is_same<R, float>::value && use_push2 && prm.enable_sort && dep == CPIC_DEPOSIT_WARP;
     }
     int prepare_reorder() override {
         if (!prm.enable_sort) return fail(CPIC_E_INVALID, "push_reorder: context was created with enable_sort=0");
+        if (push3_ok()) return CPIC_OK;      // (k_push3 keeps its own bounds, see push_reorder3)
 #if PUSH2_PLACE
         if (!use_priv()) return CPIC_OK;
 #endif
@@ -752,6 +878,7 @@ struct Ctx final : CtxBase {
             int rc = sort();
             return rc ? rc : push(k);
         }
+        if (push3_ok()) return push_reorder3(k);
         if (np == 0) return CPIC_OK;
         int rc;
 #if PUSH2_PLACE
@@ -786,6 +913,7 @@ struct Ctx final : CtxBase {
             std::swap(cell_count, cell_count2);      // cell_count: histogram of the cells the particles are in now
             hist_valid = true;
             cursor_valid = false;
+            seg_valid = false;
             want_hist = false;
         }
         return CPIC_OK;
@@ -824,7 +952,7 @@ struct Ctx final : CtxBase {
         a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC ? g.per : 0;
         a.stats = stats;
         a.hist = nullptr;
-        hist_valid = false; cursor_valid = false;
+        hist_valid = false; cursor_valid = false; seg_valid = false;
         { int rc0 = arm_leave_list(a); if (rc0) return rc0; }
         const int dep_mode = prm.deposit_mode == CPIC_DEPOSIT_AUTO ? CPIC_DEPOSIT_WARP : prm.deposit_mode;
         const bool p2 = std::is_same<R, float>::value && use_push2 && dep_mode == CPIC_DEPOSIT_WARP;
@@ -897,7 +1025,7 @@ struct Ctx final : CtxBase {
         cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
         if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
         np = n;
-        hist_valid = false; cursor_valid = false; leavers_valid = false; ghost_clean = false; want_hist = false;
+        hist_valid = false; cursor_valid = false; seg_valid = false; leavers_valid = false; ghost_clean = false; want_hist = false;
         PushArgs<R> a0 = push_args(k);
         const int32_t* cin = static_cast<const int32_t*>(in[7]);
         long long chunk = 0;
@@ -968,9 +1096,10 @@ struct Ctx final : CtxBase {
         return check_launch("k_uncenter");
     }
 
-    int scan_cells(long long n = -1) {
-        // exclusive scan of cell_count[0, n) in place (3 levels of 2048-wide tiles); n = nc, or nc + 1 (placing push)
-        if (n < 0) n = g.nc;
+    int scan_cells(long long n = -1) { return scan_buf(cell_count, n < 0 ? g.nc : n); }
+    int scan_buf(unsigned* buf, long long n) {
+        // exclusive scan of buf[0, n) in place (3 levels of 2048-wide tiles); n = nc or nc + 1
+        unsigned* const cell_count = buf;
         const long long n_l1 = (n + SCAN_TILE - 1) / SCAN_TILE, n_l2 = (n_l1 + SCAN_TILE - 1) / SCAN_TILE;
         k_scan_tile<<<(unsigned)n_l1, 256, 0, stream>>>(cell_count, cell_count, n, scan_l1);
         int rc = check_launch("k_scan_tile");
@@ -1000,7 +1129,7 @@ struct Ctx final : CtxBase {
             k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
             if ((rc = check_launch("k_cell_histogram"))) return rc;
         }
-        hist_valid = false; cursor_valid = false; leavers_valid = false;
+        hist_valid = false; cursor_valid = false; seg_valid = false; leavers_valid = false;
         if ((rc = scan_cells())) return rc;
         k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
         if ((rc = check_launch("k_sort_scatter"))) return rc;
@@ -1014,7 +1143,7 @@ struct Ctx final : CtxBase {
         if (a.count < 0 || a.count > cap) return fail(CPIC_E_CAPACITY, "init_uniform_plasma: %lld particles exceed capacity %lld", a.count, cap);
         if (a.gnx != g.nx || a.gny != g.ny) return fail(CPIC_E_INVALID, "init_uniform_plasma: x/y extents must equal the context's");
         np = a.count;
-        hist_valid = false; cursor_valid = false; leavers_valid = false; ghost_clean = true;
+        hist_valid = false; cursor_valid = false; seg_valid = false; leavers_valid = false; ghost_clean = true;
         if (np == 0) return CPIC_OK;
         k_init_uniform_plasma<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], a);
         return check_launch("k_init_uniform_plasma");
@@ -1298,7 +1427,7 @@ int cpic_set_num_particles(cpic_ctx* ctx, int64_t n) {
     CTX_HOSTNP(ctx);
     if (n < 0 || n > c->prm.max_particles) return c->fail(CPIC_E_CAPACITY, "set_num_particles: %lld out of range", (long long)n);
     c->np = n;
-    c->hist_valid = false; c->cursor_valid = false; c->leavers_valid = false; c->ghost_clean = false;
+    c->hist_valid = false; c->cursor_valid = false; c->seg_valid = false; c->leavers_valid = false; c->ghost_clean = false;
     return CPIC_OK;
 }
 

@@ -14,5 +14,5 @@ for lib in cabanapic_b200/libcabanapic_b200.so cabanapic_b200/libcabanapic_b200_
   [ -f "$lib" ] || continue
   echo "== $lib"
   CPIC_LIB=$PWD/$lib timeout 120 python tools/probe_reorder.py 256 256 64 64 4 reorder 2>&1 | tail -2
-  CPIC_LIB=$PWD/$lib timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "not full_size" 2>&1 | tail -1
+  CPIC_LIB=$PWD/$lib timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "push_reorder_teacher or sorted_steps or push_strict" 2>&1 | tail -1
 done
