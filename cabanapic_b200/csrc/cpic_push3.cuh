@@ -101,6 +101,28 @@ __device__ __forceinline__ void red_add_u32_if(bool p, unsigned* addr, unsigned 
                  : "memory");
 }
 
+#ifndef PUSH3_DUAL
+#define PUSH3_DUAL 0
+#endif
+#ifndef PUSH3_LATEPF
+#define PUSH3_LATEPF 0
+#endif
+// One 128-bit piece of an interpolator record: from the TMA-staged chunk (shared memory) or, for a foreigner whose cell
+// lies outside the chunk, from global memory -- no generic addressing (a generic pointer costs S2R SR_SWINHI / CgaCtaId
+// and 64-bit address arithmetic per tile).  The shared-memory load is unconditional (an out-of-chunk lane reads the
+// chunk's first record and discards it): a pair of complementary predicated loads makes ptxas treat the destination as
+// read-modify-write and spill it.
+template <int OFF>
+__device__ __forceinline__ float4 ld_interp(bool in, unsigned saddr, const float* gptr) {
+    float4 v;      // (not volatile: the address depends on this tile's records, which are loaded behind the chunk's barrier)
+    asm("{\n.reg .pred p;\nsetp.eq.u32 p, %6, 0;\n"
+        "ld.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %7];\n"
+        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5 + %7];\n}\n"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"(saddr), "l"(gptr), "r"((unsigned)in), "n"(OFF));
+    return v;
+}
+
 // Branch-free segmented sum of the warp's 32 deposit rows (see segsum_rows): lane -> (row group rg, entry group eg).
 // Rows of a tile's native stayers are sorted by cell; a row with cell -1 holds exact zeros and never breaks a run.
 // Lanes 24..31 count the native stayers per cell the same way (histogram of the new cells).
@@ -213,6 +235,7 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
     P2 P{one_rt};
     const float one = 1.f, one_third = (float)(1. / 3.), two_fifteenths = (float)(2. / 15.);
     int nlist = 0;
+    const unsigned sm_ip = smem_u32(sm.ip);
     unsigned long long n_mov = 0, n_cross = 0, n_wrap[6] = {0, 0, 0, 0, 0, 0};
     const PRec<float>* __restrict__ grec = a.p.rec;
     PRec<float> rzero;
@@ -277,11 +300,13 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             const unsigned iA = i0 + 2u * lane, iB = iA + 1u;
             const bool validA = iA < r1, validB = iB < r1;
             PRec<float> rA_n = rzero, rB_n = rzero;
+#if !PUSH3_LATEPF
             {   // the next tile's records: requested now, consumed next iteration (nothing may touch them before)
                 const unsigned nA = iA + 64u;
                 if (nA < r1) rA_n = grec[nA];
                 if (nA + 1u < r1) rB_n = grec[nA + 1u];
             }
+#endif
             const int cA = validA ? real_to_cell(rA.pos.w) : c0;
             const int cB = validB ? real_to_cell(rB.pos.w) : cA;
             const unsigned oA = (unsigned)(cA - c0), oB = (unsigned)(cB - c0);
@@ -321,6 +346,21 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             // whose cell lies outside the chunk
             float2 hax, hay, haz, cbx, cby, cbz;
             {
+#if PUSH3_DUAL
+                const unsigned sa = sm_ip + (inA ? oA * 80u : 0u), sb = sm_ip + (inB ? oB * 80u : 0u);
+                const float* ga = a.ip + (long long)cA * 20;
+                const float* gb = a.ip + (long long)cB * 20;
+                float fA[20], fB[20];
+#define CPIC_LDI(f, in, sx, gx)                                                                    \
+                *reinterpret_cast<float4*>(&f[0]) = ld_interp<0>(in, sx, gx);                        \
+                *reinterpret_cast<float4*>(&f[4]) = ld_interp<16>(in, sx, gx);                       \
+                *reinterpret_cast<float4*>(&f[8]) = ld_interp<32>(in, sx, gx);                       \
+                *reinterpret_cast<float4*>(&f[12]) = ld_interp<48>(in, sx, gx);                      \
+                *reinterpret_cast<float4*>(&f[16]) = ld_interp<64>(in, sx, gx);
+                CPIC_LDI(fA, inA, sa, ga)
+                CPIC_LDI(fB, inB, sb, gb)
+#undef CPIC_LDI
+#else
                 const float4* pa = inA ? reinterpret_cast<const float4*>(sm.ip + oA * 20u)
                                        : reinterpret_cast<const float4*>(a.ip + (long long)cA * 20);
                 const float4* pb = inB ? reinterpret_cast<const float4*>(sm.ip + oB * 20u)
@@ -330,6 +370,7 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                 for (int k = 0; k < 5; ++k) *reinterpret_cast<float4*>(&fA[4 * k]) = pa[k];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) *reinterpret_cast<float4*>(&fB[4 * k]) = pb[k];
+#endif
 #define F2(k) make_float2(fA[k], fB[k])
                 hax = P.mul(P.madd<FMA>(z, P.madd<FMA>(y, F2(I_D2EXDYDZ), F2(I_DEXDZ)), P.madd<FMA>(y, F2(I_DEXDY), F2(I_EX))), a.qdt_2mc);
                 hay = P.mul(P.madd<FMA>(x, P.madd<FMA>(z, F2(I_D2EYDZDX), F2(I_DEYDX)), P.madd<FMA>(z, F2(I_DEYDZ), F2(I_EY))), a.qdt_2mc);
@@ -366,6 +407,13 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             uz = P.madd<FMA>(v4, P.mdiff<FMA>(v0, cby, v1, cbx), uz);
             ux = P.add(ux, hax); uy = P.add(uy, hay); uz = P.add(uz, haz);
             const float2 pux = ux, puy = uy, puz = uz;      // the new momentum (:165-167)
+#if PUSH3_LATEPF
+            {   // the next tile's records: requested now that the interpolator registers are free, consumed next iteration
+                const unsigned nA = iA + 64u;
+                if (nA < r1) rA_n = grec[nA];
+                if (nA + 1u < r1) rB_n = grec[nA + 1u];
+            }
+#endif
 
             // ---- displacement (src/push.h:169-182)
             {
