@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --gpus N ...            # reference CPU arm (rank 0 only)
 
-metric    particle-steps/s of the whole time step (sort + interpolator load + push/move/deposit
-          + accumulator unload + Yee field advance) on the synthetic uniform thermal plasma of
+metric    particle-steps/s of the whole time step (interpolator load + push/move/deposit [+ the cell
+          ordering folded into the push] + accumulator unload + Yee field advance) on the synthetic uniform thermal plasma of
           BASELINE.json configs[4] / SURVEY.md §8(d): 256^3 cells x 64 particles/cell = 2^30
           particles, float, periodic, vth = 0.1 c, dt = 0.99 Courant.
 value     device-resident throughput (state already in HBM), CUDA events on the context's stream.
@@ -34,6 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "particle-steps/s (whole step: push+move+deposit+field advance)"      # identical in both arms
 BYTES_PER_PARTICLE_STEP = 56.0       # read 8 members (32 B) + write dx,dy,dz,ux,uy,uz (24 B), float
 FALLBACK_HBM_GBS = 6650.0            # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -52,6 +53,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1/C2/C3 side lines (N=1 only)")
+    ap.add_argument("--python-stepper", action="store_true", help="N>1: the round-1 torch stepper instead of cpic_mgpu_step")
     return ap.parse_args()
 
 
@@ -130,28 +133,74 @@ def workload(args, free_bytes=None):
     return grid, nppc, name
 
 
+class stdout_to_stderr:
+    """The reference's sources print their deck banners to stdout; the bench's stdout carries ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(grid_xy, nppc, steps, warmup, min_seconds=0.0, max_steps=None):
-    """Time the reference's own CPU implementation (oracle/_ref OpenMP build of the reference
-    sources; else the scalar C restatement) on a bounded z-thin sample of the same plasma."""
+def cpu_sample_grid(grid, nppc):
+    """C5 scaled to host RAM -- 128^3 cells x 64 ppc when the host has the memory (state + the
+    reference's own copy + one accumulator per thread, ~14 GB), else a z-thin slab of the same plasma."""
+    import psutil
+    nx, ny, nz = grid
+    avail = psutil.virtual_memory().available
+    cand = (min(nx, 128), min(ny, 128), min(nz, 128))
+    n = cand[0] * cand[1] * cand[2] * nppc
+    threads = len(os.sched_getaffinity(0))
+    need = n * 32 * 2.3 + (cand[0] + 2) * (cand[1] + 2) * (cand[2] + 2) * (48 * threads + 200)
+    if need < 0.5 * avail and threads >= 8:
+        return cand
+    return (nx, ny, min(nz, 4))
+
+
+def tiled_plasma(d, we, base=1 << 22):
+    """The synthetic plasma for a CPU timing sample: the first `base` Philox particles of the GPU generator (numpy, ~1 us
+    each) tiled over the box -- same distributions, same cell-by-cell order, different cells; generating all of them in
+    numpy would take minutes."""
+    from cabanapic_b200 import decks
+    n = d.num_particles
+    blk = decks.uniform_plasma_chunk(d, we, 0, min(base, n))
+    p = {}
+    reps = (n + len(blk["dx"]) - 1) // len(blk["dx"])
+    for m in "dx dy dz ux uy uz w".split():
+        p[m] = np.tile(blk[m], reps)[:n]
+    c = np.arange(n, dtype=np.int64) // d.nppc
+    ix, iy, iz = c % d.nx, (c // d.nx) % d.ny, c // (d.nx * d.ny)
+    p["cell"] = ((ix + 1) + (d.nx + 2) * ((iy + 1) + (d.ny + 2) * (iz + 1))).astype(np.int32)
+    return p
+
+
+def cpu_reference_run(sample_grid, nppc, steps, warmup, min_seconds=0.0, max_steps=None, one_thread=False):
+    """Time the reference's own CPU implementation (oracle/_ref: the reference's sources compiled against the
+    OpenMP Kokkos/Cabana stand-in; else the scalar C restatement) on a bounded sample of the same plasma."""
     from cabanapic_b200 import decks
     from oracle.api import Consts as OConsts, RefLib, Restatement, State
-    nx, ny = grid_xy
-    nz = 4
+    nx, ny, nz = sample_grid
     d = decks.uniform_plasma(nx, ny, nz, nppc)
     k, _, we = d.consts()
     ok = OConsts(**k.to_dict())
-    p = decks.uniform_plasma_particles(d, we)
+    p = tiled_plasma(d, we)
     s = State(nx, ny, nz, 1, d.num_particles, "f32")
     for n in p:
         s.p[n][:] = p[n]
+    del p
     sample = f"{nx}x{ny}x{nz} cells x {nppc} ppc = {d.num_particles} particles of the same plasma, float, EM"
     if RefLib.available("default", "f32", omp=True):
         # all the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1 to its workers, which would
         # silently turn the reference arm into a single-thread run
         try:
             import ctypes
-            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(len(os.sched_getaffinity(0)))
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(1 if one_thread else len(os.sched_getaffinity(0)))
         except Exception:
             pass
         R = RefLib("default", "f32", omp=True).create(s, solver=0)
@@ -171,7 +220,10 @@ def cpu_reference_run(grid_xy, nppc, steps, warmup, min_seconds=0.0, max_steps=N
         if el >= min_seconds or (max_steps and done >= max_steps):
             break
     return {"value": d.num_particles * done / el, "unit": "particle-steps/s", "cores": cores, "kind": kind,
-            "sample": sample + f", {done} steps in {el:.2f} s"}, el / done * 1e3, d.num_particles
+            "sample": sample + f", {done} steps in {el:.2f} s",
+            "what": "the reference's own src/*.cpp + headers compiled where they lie (oracle/Makefile) against an OpenMP "
+                    "Kokkos/Cabana stand-in (neither is installable offline); same loop as example/example.cpp:221-266"}, \
+        el / done * 1e3, d.num_particles
 
 
 def run_reference_arm(args):
@@ -179,14 +231,18 @@ def run_reference_arm(args):
     if rank != 0:
         return
     grid, nppc, name = workload(args)
+    sg = cpu_sample_grid(grid, nppc)
     # each "step" is one full time step of the bounded sample
-    cb, ms, npart = cpu_reference_run(grid[:2], nppc, args.steps, args.warmup, min_seconds=0.0,
-                                      max_steps=args.steps)
-    line = {"impl": "reference", "metric": "particle-steps/s (whole step: push+move+deposit+field advance)",
+    with stdout_to_stderr():
+        cb, ms, npart = cpu_reference_run(sg, nppc, args.steps, args.warmup, min_seconds=0.0, max_steps=args.steps)
+    line = {"impl": "reference", "metric": METRIC,
             "value": cb["value"], "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "sample": cb["sample"]},
+            "config": {"workload": name, "ran": cb["sample"],
+                       "note": "CPU arm: every step is one whole time step of a bounded sample of the workload (the "
+                               "full 2^30-particle box needs > 100 GB of host state and ~5 s per step); throughput is "
+                               "per particle-step, so it compares with the GPU arm's"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
@@ -221,7 +277,7 @@ def run_ours(args):
 
     if world > 1:
         from cabanapic_b200 import dist as cdist
-        runner = cdist.make_runner(d, k, we, rank, world, local, mode=args.mode, fp_mode=fp)
+        runner = cdist.make_runner(d, k, we, rank, world, local, mode=args.mode, fp_mode=fp, native=not args.python_stepper)
     else:
         runner = SingleGpu(d, k, we, local, fp)
     runner.setup()
@@ -249,6 +305,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     prof = runner.profile_result()
     launches = runner.launches_in_timed_region()
+    # parity block: the state the timed region left behind, digested on the device (collective at N > 1)
+    digest = runner.digest() if hasattr(runner, "digest") else None
     if world > 1:
         t = torch.tensor([dev_ms, wall_ms, prof["push_ms"], float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -262,7 +320,7 @@ def run_ours(args):
     push_ms_per_launch = prof["push_ms"] / args.steps
     per_launch_particles = runner.local_particles()
     achieved = BYTES_PER_PARTICLE_STEP * per_launch_particles / (push_ms_per_launch * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_push2 (push + move_p + deposit)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_push3 (push + move_p + deposit + cell ordering; block-owned cell chunks)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_particle_step": BYTES_PER_PARTICLE_STEP,
                 "particles_per_launch": per_launch_particles, "ms_per_launch": push_ms_per_launch,
@@ -289,16 +347,39 @@ def run_ours(args):
     runner.close()
 
     cpu_base = None
+    extras = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base, _, _ = cpu_reference_run((nx, ny), nppc, 2, 1, min_seconds=10.0, max_steps=200)
+        with stdout_to_stderr():
+            cpu_base, _, _ = cpu_reference_run(cpu_sample_grid((nx, ny, nz), nppc), nppc, 2, 1, min_seconds=10.0, max_steps=200)
+            try:      # BASELINE.md section 4 also asks for a 1-thread figure
+                one, _, _ = cpu_reference_run((64, 64, 16), nppc, 1, 1, min_seconds=2.0, max_steps=8, one_thread=True)
+                cpu_base["value_1thread"] = one["value"]
+                cpu_base["sample_1thread"] = one["sample"]
+            except Exception as ex:      # pragma: no cover
+                cpu_base["value_1thread"] = None
+                cpu_base["note_1thread"] = str(ex)
+    if rank == 0 and world == 1 and not args.no_extras and not args.grid:
+        with stdout_to_stderr():
+            extras = side_lines(local)
 
     if rank == 0:
-        line = {"metric": "particle-steps/s (whole step: sort+push+move+deposit+field advance)",
+        parity = None
+        if digest is not None:
+            parity = dict(digest)
+            parity["steps_taken"] = args.warmup + args.steps
+            parity["expected_particles"] = n_total
+            parity["expected_weight_sum"] = float(np.float32(we)) * n_total
+            parity["ok"] = bool(digest["particles"] == n_total and digest["cells_not_interior"] == 0 and
+                                digest["offsets_out_of_range"] == 0 and
+                                abs(digest["weight_sum"] - parity["expected_weight_sum"]) <= 1e-6 * parity["expected_weight_sum"])
+        line = {"metric": METRIC,
                 "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": name, "particles": n_total, "cells": [nx, ny, nz], "ppc": nppc,
-                           "sort_interval": sort_interval, "fp_mode": args.fp, "deposit": "shared-memory segmented sum + red.v4",
+                           "sort_interval": sort_interval, "fp_mode": args.fp,
+                           "push": "k_push3: CTA-owned cell chunks, TMA-staged interpolators, native/foreigner split, "
+                                   "branch-free segmented sum + red.v4, cell ordering folded into the push",
                            "parallelism": runner.describe(),
                            "l2": "inputs (>= 30 GB per GPU) exceed the 126 MB L2; no flush needed"},
                 "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall_ms / args.steps,
@@ -310,6 +391,10 @@ def run_ours(args):
             line["e2e"] = e2e
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if parity is not None:
+            line["parity"] = parity
+        if extras:
+            line["extra"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         # never let a teardown problem (e.g. a communicator still referenced by a captured graph) hang the run:
@@ -361,6 +446,9 @@ class SingleGpu:
     def local_particles(self):
         return self.c.num_particles
 
+    def digest(self):
+        return self.c.state_digest()
+
     def describe(self):
         return "1 GPU, whole domain"
 
@@ -400,6 +488,59 @@ class SingleGpu:
 
     def close(self):
         self.c.close()
+
+
+def side_lines(device):
+    """Side lines for the other BASELINE configs (N = 1): C2 through the C ABI, C1 / C3 through the C++ host facade
+    (examples/build/cbnpic_<deck>: the reference's own deck source, unmodified, on the facade headers) with the
+    reference's CPU build of the same deck beside it.  Bounded to a few seconds each; failures are reported, not fatal."""
+    import re
+    out = {}
+    # C2: the two-stream deck scaled to 1e8 particles on 32 cells, ES solver
+    try:
+        import cabanapic_b200 as cp
+        from cabanapic_b200 import decks
+        d = decks.two_stream_short(np.float32, orientation="x")
+        d.nppc = 3125000
+        k, _, we = d.consts()
+        n = d.num_particles
+        with cp.Context(d.nx, d.ny, d.nz, 1, max_particles=n, real=np.float32, solver=cp.SOLVER_ES_1D, device=device) as c:
+            c.upload_particles(d.initial_particles())      # the deck's initialiser on the host, as the reference runs it
+            c.upload_fields(d.initial_fields())
+            c.step(k, 8, cp.SORT_FUSED, False); c.sync()
+            c.step(k, 40, cp.SORT_FUSED, False); c.sync()
+            ms = c.last_ms(3) / 40
+        out["c2_two_stream_1e8_es"] = {"particles": n, "cells": [d.nx, d.ny, d.nz], "ms_per_step": ms,
+                                       "value": n / (ms * 1e-3), "unit": "particle-steps/s", "path": "cpic_step(CPIC_SORT_FUSED)"}
+    except Exception as ex:
+        out["c2_two_stream_1e8_es"] = {"error": str(ex)[:300]}
+    # C1 / C3 through the facade binaries
+    from oracle.api import RefLib
+    for key, exe, deck, steps in (("c1_two_stream_em_facade", "cbnpic_2stream-em", "2stream-em", 2000),
+                                  ("c3_dioctron_3d_facade", "cbnpic_dioctron_3d", "dioctron_3d", 2000)):
+        path = os.path.join(ROOT, "examples", "build", exe)
+        try:
+            if not os.path.exists(path):
+                raise RuntimeError(f"{path} not built")
+            env = dict(os.environ, CPIC_STEPS=str(steps), CPIC_ENERGY_INTERVAL="0", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)))
+            r = subprocess.run([path], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
+            m = re.search(r"#(\d+) steps of (\d+) particles in ([0-9.]+) s: ([0-9.e+]+) particle-steps/s", r.stdout)
+            if not m:
+                raise RuntimeError("no summary line: " + (r.stdout[-200:] + r.stderr[-200:]))
+            e = {"steps": int(m.group(1)), "particles": int(m.group(2)), "seconds": float(m.group(3)),
+                 "value": float(m.group(4)), "unit": "particle-steps/s", "steps_per_s": int(m.group(1)) / float(m.group(3)),
+                 "path": f"examples/build/{exe} (C++ facade over the C ABI, default settings, wall clock incl. launches)"}
+            if RefLib.available(deck, "f32"):
+                R = RefLib(deck, "f32").create_from_deck(solver=0)
+                kk, _, _ = R.deck_consts()
+                R.run(kk, 20)
+                t0 = time.perf_counter(); R.run(kk, 200); el = time.perf_counter() - t0
+                e["cpu_reference_steps_per_s"] = 200 / el
+                e["speedup_vs_cpu_reference"] = e["steps_per_s"] / (200 / el)
+            out[key] = e
+        except Exception as ex:
+            out[key] = {"error": str(ex)[:300]}
+    return out
 
 
 def main():

@@ -11,10 +11,10 @@ The Python modules are plumbing for tests and the benchmark:
 """
 from ._lib import (BOUNDARY_PERIODIC, BOUNDARY_REFLECT, DEPOSIT_ATOMIC, DEPOSIT_ATOMIC_V4, DEPOSIT_AUTO,
                    DEPOSIT_WARP, FP_CONTRACT, FP_STRICT, SOLVER_EM, SOLVER_ES_1D, SORT_FUSED, Consts, Context, CpicError,
-                   build, lib)
+                   MGPU_AUTO, MGPU_REPLICATED, MGPU_SLAB, Mgpu, build, lib)
 from .decks import Deck
 from .sim import Simulation
 
 __all__ = ["Context", "Consts", "CpicError", "Deck", "Simulation", "build", "lib", "SOLVER_EM", "SOLVER_ES_1D",
            "BOUNDARY_PERIODIC", "BOUNDARY_REFLECT", "FP_STRICT", "FP_CONTRACT", "DEPOSIT_AUTO", "DEPOSIT_ATOMIC",
-           "DEPOSIT_ATOMIC_V4", "DEPOSIT_WARP", "SORT_FUSED"]
+           "DEPOSIT_ATOMIC_V4", "DEPOSIT_WARP", "SORT_FUSED", "Mgpu", "MGPU_AUTO", "MGPU_REPLICATED", "MGPU_SLAB"]

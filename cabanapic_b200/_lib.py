@@ -133,7 +133,28 @@ def lib() -> C.CDLL:
             "cpic_launch_count": [vp, C.POINTER(i64)],
             "cpic_enable_step_profile": [vp, i32],
             "cpic_step_profile": [vp, C.POINTER(dbl), C.POINTER(i64)],
+            "cpic_state_digest": [vp, C.POINTER(dbl)],
+            # multi-GPU layer (include/cabanapic_b200_mgpu.h)
+            "cpic_mgpu_unique_id": [vp],
+            "cpic_mgpu_bootstrap_file": [C.c_char_p, i32, i32, dbl, vp],
+            "cpic_mgpu_create": [C.POINTER(Params), i32, i32, vp, i32, i64, C.POINTER(vp)],
+            "cpic_mgpu_layout": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+            "cpic_mgpu_init_uniform_plasma": [vp, i32, C.c_uint64, dbl, dbl, dbl, dbl],
+            "cpic_mgpu_reduce_accumulator": [vp],
+            "cpic_mgpu_step": [vp, C.POINTER(Consts), i64, i32, i32],
+            "cpic_mgpu_migration_counts": [vp, C.POINTER(i64)],
+            "cpic_mgpu_last_migration": [vp, C.POINTER(i64)],
+            "cpic_mgpu_energies": [vp, C.POINTER(dbl), C.POINTER(dbl)],
+            "cpic_mgpu_state_digest": [vp, C.POINTER(dbl)],
+            "cpic_mgpu_sync": [vp],
+            "cpic_mgpu_used_graph": [vp],
         }
+        L.cpic_mgpu_last_error.restype = C.c_char_p
+        L.cpic_mgpu_last_error.argtypes = [C.c_void_p]
+        L.cpic_mgpu_destroy.restype = None
+        L.cpic_mgpu_destroy.argtypes = [C.c_void_p]
+        L.cpic_mgpu_context.restype = C.c_void_p
+        L.cpic_mgpu_context.argtypes = [C.c_void_p]
         for name, args in sig.items():
             fn = getattr(L, name)
             fn.argtypes = args
@@ -151,7 +172,14 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
             "cpic_energies", "cpic_kinetic_energy", "cpic_update_ghosts", "cpic_step", "cpic_step_host", "cpic_sort_particles", "cpic_push_reorder", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
             "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
             "cpic_set_axis_periodic", "cpic_advance_b_stencil", "cpic_advance_e_stencil", "cpic_extract_z_leavers", "cpic_append_particles_device", "cpic_slab_extract_async", "cpic_slab_append_async",
-            "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile"]
+            "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile", "cpic_state_digest"]
+EXPORTED_MGPU = ["cpic_mgpu_last_error", "cpic_mgpu_unique_id", "cpic_mgpu_bootstrap_file", "cpic_mgpu_create",
+                 "cpic_mgpu_destroy", "cpic_mgpu_context", "cpic_mgpu_layout", "cpic_mgpu_init_uniform_plasma",
+                 "cpic_mgpu_reduce_accumulator", "cpic_mgpu_step", "cpic_mgpu_migration_counts", "cpic_mgpu_last_migration",
+                 "cpic_mgpu_energies", "cpic_mgpu_state_digest", "cpic_mgpu_sync", "cpic_mgpu_used_graph"]
+MGPU_REPLICATED, MGPU_SLAB, MGPU_AUTO = 0, 1, 2
+DIGEST_NAMES = ["particles", "weight_sum", "cells_not_interior", "offsets_out_of_range", "kinetic_energy",
+                "e_energy", "b_energy", "migrated"]
 
 
 def _p(a):
@@ -182,10 +210,29 @@ class Context:
         self.nc = (nx + 2 * ng) * (ny + 2 * ng) * (nz + 2 * ng)
         self.solver = solver
 
+    @classmethod
+    def borrowed(cls, handle, nx, ny, nz, real, solver=SOLVER_EM):
+        """Wrap a cpic_ctx owned by somebody else (cpic_mgpu_context): never destroyed from here."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.real = np.dtype(real)
+        self.h = C.c_void_p(handle)
+        self._borrowed = True
+        self.nx, self.ny, self.nz, self.ng = nx, ny, nz, 1
+        self.nc = (nx + 2) * (ny + 2) * (nz + 2)
+        self.solver = solver
+        return self
+
     def close(self):
         if getattr(self, "h", None):
-            self.L.cpic_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                self.L.cpic_destroy(self.h)
             self.h = None
+
+    def state_digest(self):
+        d = (C.c_double * 8)()
+        self._ck(self.L.cpic_state_digest(self.h, d))
+        return dict(zip(DIGEST_NAMES, list(d)))
 
     def __del__(self):
         try:
@@ -412,3 +459,88 @@ class Context:
         n = C.c_int64()
         self._ck(self.L.cpic_launch_count(self.h, C.byref(n)))
         return n.value
+
+
+class Mgpu:
+    """One rank of the native multi-GPU layer (include/cabanapic_b200_mgpu.h): host C++ + NCCL inside the library.
+    The launcher only has to distribute the 128-byte NCCL id (``unique_id()`` on rank 0)."""
+
+    def __init__(self, nx, ny, nz, rank, world, unique_id: bytes | None, mode=MGPU_AUTO, max_particles=0, real=np.float32,
+                 solver=SOLVER_EM, device=0, fp_mode=FP_STRICT, send_capacity=0):
+        self.L = lib()
+        self.real = np.dtype(real)
+        self.params = Params(nx=nx, ny=ny, nz=nz, ng=1, real_bytes=self.real.itemsize, solver=solver,
+                             boundary=BOUNDARY_PERIODIC, device=device, fp_mode=fp_mode, deposit_mode=DEPOSIT_AUTO,
+                             max_particles=int(max_particles), enable_sort=1)
+        h = C.c_void_p()
+        idbuf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        rc = self.L.cpic_mgpu_create(C.byref(self.params), rank, world, idbuf, mode, int(send_capacity), C.byref(h))
+        if rc != 0:
+            raise CpicError(rc, (self.L.cpic_mgpu_last_error(None) or b"").decode())
+        self.h = h
+        self.rank, self.world = rank, world
+        mo, z0, nzl = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.L.cpic_mgpu_layout(self.h, C.byref(mo), C.byref(z0), C.byref(nzl)))
+        self.mode, self.z0, self.nzl = mo.value, z0.value, nzl.value
+        self.ctx = Context.borrowed(self.L.cpic_mgpu_context(self.h), nx, ny, self.nzl, real, solver)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        L = lib()
+        buf = C.create_string_buffer(128)
+        rc = L.cpic_mgpu_unique_id(buf)
+        if rc != 0:
+            raise CpicError(rc, (L.cpic_mgpu_last_error(None) or b"").decode())
+        return buf.raw
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CpicError(rc, (self.L.cpic_mgpu_last_error(self.h) or b"").decode())
+
+    def init_uniform_plasma(self, nppc, seed=12345, vth=(0.1, 0.1, 0.1), weight=1.0):
+        self._ck(self.L.cpic_mgpu_init_uniform_plasma(self.h, nppc, seed, vth[0], vth[1], vth[2], weight))
+
+    def step(self, k: Consts, nsteps=1, sort_interval=SORT_FUSED, use_graph=False):
+        self._ck(self.L.cpic_mgpu_step(self.h, C.byref(k), nsteps, sort_interval, 1 if use_graph else 0))
+
+    def reduce_accumulator(self):
+        self._ck(self.L.cpic_mgpu_reduce_accumulator(self.h))
+
+    def migration_counts(self):
+        a = (C.c_int64 * 2)()
+        self._ck(self.L.cpic_mgpu_migration_counts(self.h, a))
+        return int(a[0]), int(a[1])
+
+    def last_migration(self):
+        a = (C.c_int64 * 2)()
+        self._ck(self.L.cpic_mgpu_last_migration(self.h, a))
+        return int(a[0]), int(a[1])
+
+    def energies(self):
+        e, b = C.c_double(), C.c_double()
+        self._ck(self.L.cpic_mgpu_energies(self.h, C.byref(e), C.byref(b)))
+        return e.value, b.value
+
+    def state_digest(self):
+        d = (C.c_double * 8)()
+        self._ck(self.L.cpic_mgpu_state_digest(self.h, d))
+        return dict(zip(DIGEST_NAMES, list(d)))
+
+    def sync(self):
+        self._ck(self.L.cpic_mgpu_sync(self.h))
+
+    @property
+    def used_graph(self):
+        return bool(self.L.cpic_mgpu_used_graph(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.close()
+            self.L.cpic_mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

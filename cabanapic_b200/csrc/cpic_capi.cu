@@ -39,6 +39,8 @@ struct CtxBase {
     long long launches = 0;
     cudaEvent_t ev[8]{};   // 0/1 push, 2/3 sort, 4/5 field side, 6/7 step
     bool ev_valid[4] = {false, false, false, false};
+    bool capturing = false;    // the stream is being captured into a CUDA graph (cpic_mgpu_step): timing events become external nodes
+    void rec(int i) { cudaEventRecordWithFlags(ev[i], stream, capturing ? cudaEventRecordExternal : cudaEventRecordDefault); }
     bool want_stats = false;
     bool want_hist = false;    // set by cpic_step before a push that is followed by a sort
     bool hist_valid = false;   // cell_count holds the histogram of the current cells (from the last push)
@@ -89,6 +91,7 @@ struct CtxBase {
     virtual int uncenter(double qdt_2mc) = 0;
     virtual int energies_async(double* dev_out2) = 0;
     virtual int kinetic_async(double* dev_out) = 0;
+    virtual int digest_async(double* dev_out8) = 0;     // [0..4] from k_state_digest, [5] [6] field energy sums (not halved)
     virtual int update_ghosts(int which) = 0;
     virtual int sort() = 0;
     virtual int push_reorder(const cpic_consts& k) = 0;
@@ -103,7 +106,6 @@ struct CtxBase {
     virtual int slab_append_async(const void* buf, long long cap, const long long* count_dev) = 0;
     virtual bool few_cells() const = 0;   // grid small enough for the block-private accumulator (k_push2<PRIV>)
     virtual int sync_np() = 0;      // device-count mode -> host-count mode (synchronises); no-op otherwise
-    bool skip_dense = false;        // PUSH2_PLACE builds: cpic_step(FUSED) keeps the store in segment form between calls
     long long fb_steps = 0;         // steps taken in the few-cells fallback of CPIC_SORT_FUSED (sort when % 8 == 0)
     bool dev_count = false;         // slab mode: np lives in dc[0] on the device, the host's np is stale
     virtual int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
@@ -146,9 +148,6 @@ struct Ctx final : CtxBase {
             for (auto& e : ev) if (e) cudaEventDestroy(e);
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer); cudaFree(fields); cudaFree(interp); cudaFree(acc);
             cudaFree(seg[0]); cudaFree(seg[1]); cudaFree(cursor3); cudaFree(work3); cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count); cudaFree(dc);
-#if PUSH2_PLACE
-            cudaFree(seg_start); cudaFree(over_count); cudaFree(place_info);
-#endif
             for (auto b : hs_buf) cudaFree(b);
             for (auto e : hs_ev) if (e) cudaEventDestroy(e);
             if (hs_up) cudaStreamDestroy(hs_up);
@@ -196,7 +195,7 @@ struct Ctx final : CtxBase {
         if ((rc = cuda(cudaMalloc(&interp, (size_t)g.nc * S * sizeof(R)), "cudaMalloc(interpolators)"))) return rc;
         if ((rc = cuda(cudaMalloc(&acc, (size_t)g.nc * 12 * sizeof(R)), "cudaMalloc(accumulators)"))) return rc;
         if ((rc = cuda(cudaMalloc(&bad, sizeof(unsigned)), "cudaMalloc"))) return rc;
-        if ((rc = cuda(cudaMalloc(&en_dev, 2 * sizeof(double)), "cudaMalloc"))) return rc;
+        if ((rc = cuda(cudaMalloc(&en_dev, 8 * sizeof(double)), "cudaMalloc"))) return rc;
         if ((rc = cuda(cudaMalloc(&stats, 8 * sizeof(unsigned long long)), "cudaMalloc"))) return rc;
         if (prm.enable_sort) {
             n_l1 = (g.nc + 1 + SCAN_TILE - 1) / SCAN_TILE;       // (+1: the placing push scans a sentinel entry as well)
@@ -448,9 +447,6 @@ struct Ctx final : CtxBase {
         return CPIC_OK;
     }
     int sync_np() override {
-#if PUSH2_PLACE
-        { int rcd = make_dense(); if (rcd) return rcd; }
-#endif
         if (!dev_count) return CPIC_OK;
         long long h[4] = {0, 0, 0, 0};
         int rc;
@@ -576,6 +572,15 @@ struct Ctx final : CtxBase {
         k_kinetic_energy<R><<<nb, 256, 0, stream>>>(P[cur], np, dev_out);
         return check_launch("k_kinetic_energy");
     }
+    int digest_async(double* dev_out8) override {
+        cudaMemsetAsync(dev_out8, 0, 8 * sizeof(double), stream);
+        unsigned nb = blocks_for(dev_count ? cap : std::max<long long>(np, 1));
+        if (nb > 148 * 8) nb = 148 * 8;
+        k_state_digest<R><<<nb, 256, 0, stream>>>(P[cur], np, dev_count ? dc : nullptr, g, dev_out8);
+        int rc = check_launch("k_state_digest");
+        if (rc) return rc;
+        return energies_async(dev_out8 + 5);
+    }
     double* energy_scratch() override { return en_dev; }
     unsigned long long* stats_dev() override { return stats; }
 
@@ -645,90 +650,6 @@ struct Ctx final : CtxBase {
     // The reordering push (cpic_push2.cuh, REORD): cpic_push + the cell ordering of the particle store in one
     // pass.  prepare_reorder() makes cell_count the exclusive scan of the current cells' histogram (from the
     // previous reordering push when there was one); push_reorder() consumes it.
-#if PUSH2_PLACE
-    // ---- experimental placement by the NEW cell (cpic_push2.cuh, PUSH2_PLACE)
-    unsigned* seg_start = nullptr;      // nc + 1: immutable segment starts of the push in flight
-    unsigned* over_count = nullptr;
-    long long* place_info = nullptr;    // [0] extent of the store (segments + tail) [1] error flags
-    bool placed = false;                // P[cur] has segment form: holes (cell -1) and an overflow tail
-    bool place_ok() const {
-        return can_reorder() && !use_priv() && (g.per & 4) && prm.boundary == CPIC_BOUNDARY_PERIODIC && !dev_count && !want_stats &&
-               cap >= np + g.nc + np / 12 + 4096;
-    }
-    int push_place(const cpic_consts& k) {
-        int rc;
-        if (!seg_start) {
-            if ((rc = cuda(cudaMalloc(&seg_start, (size_t)(g.nc + 1) * sizeof(unsigned)), "cudaMalloc(seg_start)"))) return rc;
-            if ((rc = cuda(cudaMalloc(&over_count, sizeof(unsigned)), "cudaMalloc"))) return rc;
-            if ((rc = cuda(cudaMalloc(&place_info, 2 * sizeof(long long)), "cudaMalloc"))) return rc;
-            cudaMemsetAsync(place_info, 0, 2 * sizeof(long long), stream);
-        }
-        // capacities (counts rounded up to even) -> segment starts; cell_count becomes the mutable cursor
-        if (!hist_valid) {          // only possible on a dense store (a placing push always leaves the histogram)
-            cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
-            cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
-            k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
-            if ((rc = check_launch("k_cell_histogram"))) return rc;
-        }
-        hist_valid = false; cursor_valid = false;
-        k_even_caps<<<blocks_for(g.nc + 1), 256, 0, stream>>>(cell_count, g.nc);
-        if ((rc = check_launch("k_even_caps"))) return rc;
-        if ((rc = scan_cells(g.nc + 1))) return rc;
-        cudaMemcpyAsync(seg_start, cell_count, (size_t)(g.nc + 1) * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream);
-        cudaMemsetAsync(over_count, 0, sizeof(unsigned), stream);
-        if constexpr (std::is_same<R, float>::value) {
-            PushArgs<float> a = push_args(k);
-            a.leave_list = nullptr;
-            a.dst = P[cur ^ 1];
-            a.cursor = cell_count;
-            a.hist = cell_count2;
-            a.seg_start = seg_start; a.over = over_count; a.ncells = (int)g.nc; a.dst_cap = (unsigned)cap;
-            if (placed) { a.np_dev = place_info; a.np = cap; }
-            cudaMemsetAsync(cell_count2, 0, (size_t)g.nc * sizeof(unsigned), stream);
-            cudaEventRecord(ev[0], stream);
-            const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
-            const float aq = fabsf((float)a.qdt_2mc);
-            const bool fd = push2_fastds && (aq == 0.f || (aq > 1e-12f && aq < 1e12f));
-            if (fd) rc = fma ? launch_push2h<true, false, true, true, true>(a) : launch_push2h<false, false, true, true, true>(a);
-            else rc = fma ? launch_push2h<true, false, false, true, true>(a) : launch_push2h<false, false, false, true, true>(a);
-            cudaEventRecord(ev[1], stream);
-            ev_valid[0] = true;
-            if (rc) return rc;
-            k_place_finish<R><<<blocks_for(g.nc), 256, 0, stream>>>(P[cur ^ 1], cell_count, seg_start, g.nc, over_count, cap, place_info);
-            if ((rc = check_launch("k_place_finish"))) return rc;
-            if (getenv("CPIC_PLACE_DEBUG")) {
-                long long h[2]; unsigned ov = 0, t = 0;
-                cudaStreamSynchronize(stream);
-                cudaMemcpy(h, place_info, sizeof h, cudaMemcpyDeviceToHost);
-                cudaMemcpy(&ov, over_count, sizeof ov, cudaMemcpyDeviceToHost);
-                cudaMemcpy(&t, seg_start + g.nc, sizeof t, cudaMemcpyDeviceToHost);
-                fprintf(stderr, "[place] np %lld  segments %u  tail slots %u  extent %lld  err %lld\n", np, t, ov, h[0], h[1]);
-            }
-            cur ^= 1;
-            std::swap(cell_count, cell_count2);
-            hist_valid = true;
-            placed = true;
-            want_hist = false;
-        }
-        return CPIC_OK;
-    }
-    // segment form -> dense, cell-ordered store (everything but the placing push expects that)
-    int make_dense() {
-        if (!placed || skip_dense) return CPIC_OK;
-        int rc;
-        // cell_count = histogram of the current cells (left by the placing push) -> offsets -> scatter the valid records
-        if ((rc = scan_cells())) return rc;
-        k_sort_scatter_ext<R><<<148 * 16, 256, 0, stream>>>(P[cur], P[cur ^ 1], place_info, cell_count);
-        if ((rc = check_launch("k_sort_scatter_ext"))) return rc;
-        cur ^= 1;
-        placed = false; hist_valid = false; cursor_valid = false; leavers_valid = false;
-        long long h[2] = {0, 0};
-        if ((rc = cuda(cudaMemcpyAsync(h, place_info, sizeof h, cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
-        if ((rc = cuda(cudaStreamSynchronize(stream), "make_dense"))) return rc;
-        if (h[1]) { cudaMemsetAsync(place_info, 0, 2 * sizeof(long long), stream); return fail(CPIC_E_CAPACITY, "push_reorder: the overflow tail of the placing push exceeded the store capacity %lld", cap); }
-        return CPIC_OK;
-    }
-#endif
     // ---- block-owned reordering push (cpic_push3.cuh): chunks of cells per CTA, TMA-staged interpolators
     unsigned* seg[2] = {nullptr, nullptr};   // exclusive scans (nc + 1 entries + pad): segment bounds of the store, ping-pong
     unsigned* cursor3 = nullptr;             // the mutable copy of the destination bounds the push claims slots from
@@ -774,15 +695,16 @@ struct Ctx final : CtxBase {
             cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
             k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
             if ((rc = check_launch("k_cell_histogram"))) return rc;
+            if ((rc = check_bad_cells("push_reorder"))) return rc;
             hist_valid = true;
         }
-        cudaEventRecord(ev[2], stream);
+        rec(2);
         if ((rc = scan_hist_into(seg[seg_cur]))) return rc;
         if ((rc = cuda(cudaMemcpyAsync(cursor3, seg[seg_cur], (size_t)g.nc * sizeof(unsigned), cudaMemcpyDeviceToDevice, stream), "D2D cursor"))) return rc;
         k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cursor3);
         if ((rc = check_launch("k_sort_scatter"))) return rc;
         cur ^= 1;
-        cudaEventRecord(ev[3], stream);
+        rec(3);
         ev_valid[1] = true;
         cursor_valid = false; leavers_valid = false;
         seg_valid = true;
@@ -831,14 +753,14 @@ struct Ctx final : CtxBase {
             q.nchunks = p3_cpp * g.gz; q.nc = (int)g.nc;
             q.work = work3;
             if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
-            cudaEventRecord(ev[0], stream);
+            rec(0);
             const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
             const float aq = fabsf((float)q.a.qdt_2mc);
             const bool fd = push2_fastds && (aq == 0.f || (aq > 1e-12f && aq < 1e12f));
             if (want_stats) rc = fma ? launch_push3<true, true, false>(q) : launch_push3<false, true, false>(q);
             else if (fd) rc = fma ? launch_push3<true, false, true>(q) : launch_push3<false, false, true>(q);
             else rc = fma ? launch_push3<true, false, false>(q) : launch_push3<false, false, false>(q);
-            cudaEventRecord(ev[1], stream);
+            rec(1);
             ev_valid[0] = true;
             if (rc) return rc;
             cur ^= 1;
@@ -857,16 +779,14 @@ struct Ctx final : CtxBase {
     int prepare_reorder() override {
         if (!prm.enable_sort) return fail(CPIC_E_INVALID, "push_reorder: context was created with enable_sort=0");
         if (push3_ok()) return CPIC_OK;      // (k_push3 keeps its own bounds, see push_reorder3)
-#if PUSH2_PLACE
-        if (!use_priv()) return CPIC_OK;
-#endif
-        if (np == 0 || cursor_valid) return CPIC_OK;
+        if ((np == 0 && !dev_count) || cursor_valid) return CPIC_OK;
         int rc;
         if (!hist_valid) {
             cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
             cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
             k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
             if ((rc = check_launch("k_cell_histogram"))) return rc;
+            if ((rc = check_bad_cells("push_reorder"))) return rc;
         }
         hist_valid = false;
         if ((rc = scan_cells())) return rc;
@@ -879,16 +799,8 @@ struct Ctx final : CtxBase {
             return rc ? rc : push(k);
         }
         if (push3_ok()) return push_reorder3(k);
-        if (np == 0) return CPIC_OK;
+        if (np == 0 && !dev_count) return CPIC_OK;      // (device-count mode: the host's np is stale)
         int rc;
-#if PUSH2_PLACE
-        if (place_ok()) return push_place(k);
-        if (!use_priv()) {          // (this build's REORD kernels place by new cell: no old-style reordering push to fall back to)
-            if ((rc = make_dense())) return rc;
-            rc = sort();
-            return rc ? rc : push(k);
-        }
-#endif
         if ((rc = prepare_reorder())) return rc;
         if constexpr (std::is_same<R, float>::value) {
             PushArgs<float> a = push_args(k);
@@ -899,14 +811,14 @@ struct Ctx final : CtxBase {
             if (dev_count) { a.np_dev = dc; a.np = cap; }      // (a.np then only sizes the grid)
             cudaMemsetAsync(cell_count2, 0, (size_t)g.nc * sizeof(unsigned), stream);
             if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
-            cudaEventRecord(ev[0], stream);
+            rec(0);
             const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;
             const float aq = fabsf((float)a.qdt_2mc);
             const bool fd = push2_fastds && (aq == 0.f || (aq > 1e-12f && aq < 1e12f));
             if (want_stats) rc = fma ? launch_push2r<true, true, false>(a) : launch_push2r<false, true, false>(a);
             else if (fd) rc = fma ? launch_push2r<true, false, true>(a) : launch_push2r<false, false, true>(a);
             else rc = fma ? launch_push2r<true, false, false>(a) : launch_push2r<false, false, false>(a);
-            cudaEventRecord(ev[1], stream);
+            rec(1);
             ev_valid[0] = true;
             if (rc) return rc;
             cur ^= 1;
@@ -931,19 +843,13 @@ struct Ctx final : CtxBase {
         a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         a.np_dev = nullptr;
-        a.seg_start = nullptr; a.over = nullptr; a.ncells = 0; a.dst_cap = 0;
         a.priv_nc = use_priv() ? (int)g.nc : 0;
-        a.ko = 0;
-#ifdef PUSH2_KO_RT
-        if (const char* e = getenv("CPIC_PUSH2_KO")) a.ko = atoi(e);
-#endif
         return a;
     }
     int push(const cpic_consts& k) override {
         if (np == 0) return CPIC_OK;
         PushArgs<R> a;
-        a.ko = 0; a.np_dev = nullptr; a.priv_nc = use_priv() ? (int)g.nc : 0;
-        a.seg_start = nullptr; a.over = nullptr; a.ncells = 0; a.dst_cap = 0;
+        a.np_dev = nullptr; a.priv_nc = use_priv() ? (int)g.nc : 0;
         a.dst = P[cur]; a.cursor = nullptr;
         a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
         a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
@@ -964,9 +870,9 @@ struct Ctx final : CtxBase {
         want_hist = false;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
-        cudaEventRecord(ev[0], stream);
+        rec(0);
         const int rc = launch_inplace(a);
-        cudaEventRecord(ev[1], stream);
+        rec(1);
         ev_valid[0] = true;
         return rc;
     }
@@ -1016,7 +922,7 @@ struct Ctx final : CtxBase {
         if (n < 0 || n > cap) return fail(CPIC_E_CAPACITY, "step_host: %lld particles exceed capacity %lld", n, cap);
         int rc;
         if ((rc = ensure_host_stream())) return rc;
-        cudaEventRecord(ev[6], stream);
+        rec(6);
         // fields first: the interpolators every chunk's push gathers from (example/example.cpp:233-236)
         for (int m = 0; m < F_N; ++m)
             if ((rc = cuda(cudaMemcpyAsync(fields + (long long)m * nc_pad, fin[m], (size_t)g.nc * sizeof(R), cudaMemcpyHostToDevice, stream), "H2D fields"))) return rc;
@@ -1077,7 +983,7 @@ struct Ctx final : CtxBase {
                 if (fout[m] && (rc = cuda(cudaMemcpyAsync(fout[m], fields + (long long)m * nc_pad, (size_t)g.nc * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H fields"))) return rc;
         unsigned nbad = 0;
         if ((rc = cuda(cudaMemcpyAsync(&nbad, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
-        cudaEventRecord(ev[7], stream);
+        rec(7);
         ev_valid[3] = true;
         if ((rc = cuda(cudaStreamSynchronize(stream), "step_host"))) return rc;
         if ((rc = cuda(cudaStreamSynchronize(hs_dn), "step_host (D2H)"))) return rc;
@@ -1118,23 +1024,34 @@ struct Ctx final : CtxBase {
         }
         return CPIC_OK;
     }
+    // the histogram kernel counts out-of-range cell indices (set_num_particles over uninitialised records, writes through
+    // device_ptr): report them instead of scattering with them
+    int check_bad_cells(const char* what) {
+        unsigned nbad = 0;
+        int rc;
+        if ((rc = cuda(cudaMemcpyAsync(&nbad, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(stream), what))) return rc;
+        if (nbad) return fail(CPIC_E_BAD_CELL, "%s: %u particles have a cell index outside [0,%lld)", what, nbad, g.nc);
+        return CPIC_OK;
+    }
     int sort() override {
         if (!prm.enable_sort) return fail(CPIC_E_INVALID, "sort_particles: context was created with enable_sort=0");
         if (np == 0) return CPIC_OK;
         int rc;
-        cudaEventRecord(ev[2], stream);
+        rec(2);
         if (!hist_valid) {
             cudaMemsetAsync(cell_count, 0, (size_t)g.nc * sizeof(unsigned), stream);
             cudaMemsetAsync(bad, 0, sizeof(unsigned), stream);
             k_cell_histogram<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], np, g.nc, cell_count, bad);
             if ((rc = check_launch("k_cell_histogram"))) return rc;
+            if ((rc = check_bad_cells("sort_particles"))) return rc;
         }
         hist_valid = false; cursor_valid = false; seg_valid = false; leavers_valid = false;
         if ((rc = scan_cells())) return rc;
         k_sort_scatter<R><<<blocks_for(np), 256, 0, stream>>>(P[cur], P[cur ^ 1], np, cell_count);
         if ((rc = check_launch("k_sort_scatter"))) return rc;
         cur ^= 1;
-        cudaEventRecord(ev[3], stream);
+        rec(3);
         ev_valid[1] = true;
         return CPIC_OK;
     }
@@ -1328,14 +1245,13 @@ int cpic_kinetic_energy(cpic_ctx* ctx, double* out) {
 
 int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, double* energies) {
     CTX_OR_FAIL(ctx);
-    c->skip_dense = sort_interval == CPIC_SORT_FUSED;
-    { const int rc_np_ = c->sync_np(); c->skip_dense = false; if (rc_np_) return rc_np_; }
+    { const int rc_np_ = c->sync_np(); if (rc_np_) return rc_np_; }
     if (!k || nsteps < 0 || sort_interval < CPIC_SORT_FUSED) return c->fail(CPIC_E_INVALID, "step: bad arguments");
     int rc = CPIC_OK;
     double* en = nullptr;
     if (energies && nsteps > 0)
         if ((rc = c->cuda(cudaMalloc(&en, (size_t)nsteps * 2 * sizeof(double)), "cudaMalloc(energies)"))) return rc;
-    cudaEventRecord(c->ev[6], c->stream);
+    c->rec(6);
     const double hx = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->px) : 0.5 * k->px;
     const double hy = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->py) : 0.5 * k->py;
     const double hz = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->pz) : 0.5 * k->pz;
@@ -1373,7 +1289,7 @@ int cpic_step(cpic_ctx* ctx, const cpic_consts* k, int64_t nsteps, int32_t sort_
         if (!rc && en) rc = c->energies_async(en + 2 * s);
         if (prof) cudaEventRecord(c->prof_ev[5 * s + 4], c->stream);
     }
-    cudaEventRecord(c->ev[7], c->stream);
+    c->rec(7);
     c->ev_valid[3] = true;
     if (!rc && en) {
         rc = c->cuda(cudaMemcpyAsync(energies, en, (size_t)nsteps * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream), "D2H energies");
@@ -1528,3 +1444,5 @@ int cpic_launch_count(cpic_ctx* ctx, int64_t* launches) {
 }
 
 }  // extern "C"
+
+#include "cpic_mgpu.cuh"

@@ -93,4 +93,37 @@ __global__ void __launch_bounds__(256) k_kinetic_energy(Particles<R> p, long lon
     }
 }
 
+// State digest (bench / multi-GPU parity block): out[0] particles, [1] sum of weights, [2] particles whose cell is not
+// an interior voxel, [3] particles with an offset outside [-1,1], [4] kinetic energy -- one pass, double accumulation.
+// np_dev (optional): the particle count lives on the device (slab mode).
+template <class R>
+__global__ void __launch_bounds__(256) k_state_digest(Particles<R> p, long long np, const long long* __restrict__ np_dev,
+                                                      Grid g, double* __restrict__ out) {
+    if (np_dev) np = *np_dev;
+    double v[5] = {0, 0, 0, 0, 0};
+    for (long long n = blockIdx.x * 256LL + threadIdx.x; n < np; n += (long long)gridDim.x * 256) {
+        const PRec<R> r = p.rec[n];
+        const int c = real_to_cell(r.pos.w);
+        const int ix = c % g.gx, iy = (c / g.gx) % g.gy, iz = c / (g.gx * g.gy);
+        const bool interior = c >= 0 && ix >= g.ng && ix < g.nx + g.ng && iy >= g.ng && iy < g.ny + g.ng && iz >= g.ng && iz < g.nz + g.ng;
+        const bool inside = fabs((double)r.pos.x) <= 1.0 && fabs((double)r.pos.y) <= 1.0 && fabs((double)r.pos.z) <= 1.0;
+        const double u2 = (double)r.mom.x * r.mom.x + (double)r.mom.y * r.mom.y + (double)r.mom.z * r.mom.z;
+        v[0] += 1.0; v[1] += (double)r.mom.w; v[2] += interior ? 0.0 : 1.0; v[3] += inside ? 0.0 : 1.0;
+        v[4] += (double)r.mom.w * (u2 / (sqrt(1.0 + u2) + 1.0));
+    }
+    __shared__ double se[8][5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0) se[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += se[w][threadIdx.x];
+        atomicAdd(out + threadIdx.x, t);
+    }
+}
+
 }  // namespace cpic

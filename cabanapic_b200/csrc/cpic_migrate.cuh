@@ -202,6 +202,7 @@ template <class R>
 __global__ void __launch_bounds__(256) k_append_dev(Particles<R> p, SendBuf<R> b, long long cap, const long long* __restrict__ m_ptr,
                                                     long long store_cap, long long nc, unsigned* __restrict__ hist,
                                                     long long* __restrict__ dc) {
+    if (dc[1]) return;      // an earlier step of this migration flagged an error: leave the store alone (reported by sync_np)
     const long long m = *m_ptr, np = dc[0];
     if (m < 0 || m > cap || np + m > store_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) dc[1] |= 4; return; }
     for (long long j = blockIdx.x * 256LL + threadIdx.x; j < m; j += gridDim.x * 256LL) {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(256) k_append_dev(Particles<R> p, SendBuf<R> b
     }
 }
 __global__ void k_append_finish_dev(const long long* __restrict__ m_ptr, long long* __restrict__ dc) {
-    if (!(dc[1] & 4)) dc[0] += *m_ptr;
+    if (!dc[1]) dc[0] += *m_ptr;
 }
 
 // Struct-of-arrays exchange buffer (SendBuf, or a staging chunk of a host transfer) <-> records.

@@ -46,30 +46,9 @@ struct PushArgs {
     unsigned* leave_count;
     unsigned leave_cap;
     int leave_lo, leave_hi;
-    // PUSH2_PLACE (experimental): placement by the NEW cell -- immutable segment starts (ncells + 1 entries, the last
-    // one = start of the overflow tail), overflow counter, capacity of dst
-    const unsigned* seg_start;
-    unsigned* over;
-    int ncells;
-    unsigned dst_cap;
     int priv_nc;               // > 0: k_push2<PRIV> keeps a block-private accumulator (+ histogram) of this many cells in shared memory
     const long long* np_dev;   // optional: the particle count lives on the device (overrides np; k_push2 only)
-    int ko;   // developer knock-out mask (timing studies; honoured only by builds with -DPUSH2_KO_RT, see cpic_push2.cuh)
 };
-// Knock-outs for timing studies (results are wrong): compile-time mask PUSH2_KO, or with -DPUSH2_KO_RT the
-// run-time mask a.ko (env CPIC_PUSH2_KO) so that one knocked-out step can be timed on a steady-state store.
-//   1 no first-streak deposit   2 no record stores   4 every gather reads cell 0/1   8 no slot claims
-//   16 movers not drained       32 no straddling-pair deposit path   64 drain: no reductions
-//   128 drain: no position store / histogram atomic   256 first streak: summed but not reduced
-//   512 no histogram atomics in the main path
-#ifndef PUSH2_KO
-#define PUSH2_KO 0
-#endif
-#ifdef PUSH2_KO_RT
-#define CPIC_KO(bit) (a.ko & (bit))
-#else
-#define CPIC_KO(bit) (PUSH2_KO & (bit))
-#endif
 
 // ---------------------------------------------------------------------------------------
 // The 12 quadrant currents of one streak.  Reference: CALC_J, src/push.h:218-232 and
@@ -351,36 +330,8 @@ struct WarpMoverList {
     unsigned idx[CAP];   // global particle index (< 2^31)
 };
 
-// PUSH2_PLACE: slots of the overflow tail are handed out per warp from chunks of TAIL_CHUNK claimed with ONE global
-// atomic each (a single counter hit once per overflowing particle serialises the machine: 11.8 ms instead of 5).
-// The unused rest of a retired chunk is marked invalid (cell -1).  All 32 lanes call; warp-uniform state.
-constexpr unsigned TAIL_CHUNK = 64;
-struct WarpTail { unsigned base, used; };
-template <class R>
-__device__ __forceinline__ void warp_tail_retire(const WarpTail& t, const PushArgs<R>& a, int lane) {
-    if (t.base == 0xffffffffu) return;
-    for (unsigned s = t.used + lane; s < TAIL_CHUNK; s += 32)
-        if (t.base + s < a.dst_cap) a.dst.rec[t.base + s].pos.w = cell_to_real(-1, R(0));
-}
-template <class R>
-__device__ __forceinline__ unsigned warp_tail_slot(WarpTail& t, bool want, const PushArgs<R>& a, int lane) {
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (!m) return 0u;
-    const unsigned k = __popc(m);
-    if (t.used + k > TAIL_CHUNK) {
-        warp_tail_retire(t, a, lane);
-        unsigned b = 0;
-        if (lane == 0) b = a.seg_start[a.ncells] + atomicAdd(a.over, TAIL_CHUNK);
-        t.base = __shfl_sync(0xffffffffu, b, 0);
-        t.used = 0;
-    }
-    const unsigned slot = t.base + t.used + __popc(m & ((1u << lane) - 1u));
-    t.used += k;
-    return slot;
-}
-
-// PUSH2_PLACE: the drain writes the whole record of a mover (into the segment of its new cell), so the list also
-// carries the new momentum and the weight
+// the reordering push of k_push3 writes a mover's whole record from the drain, so its list also carries the new
+// momentum and the weight
 template <class R, int CAP = MOVER_CAP>
 struct WarpMoverListP : WarpMoverList<R, CAP> {
     R ux[CAP], uy[CAP], uz[CAP], w[CAP];
@@ -390,34 +341,29 @@ struct WarpMoverListP : WarpMoverList<R, CAP> {
 // src/move_p.h:93-371 -- streak, deposit into the current cell, then either stop (end of
 // track) or cross the face into the neighbour and continue.
 // OUTOFPLACE: the list's idx are slots of a.dst (reordering push) and the cell is always written.
-template <class R, bool FMA, int DEPOSIT, bool STATS, class List, bool OUTOFPLACE = false, bool PRIV = false, bool PLACE = false>
+template <class R, bool FMA, int DEPOSIT, bool STATS, class List, bool OUTOFPLACE = false, bool PRIV = false>
 __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int first, int count,
                                              int lane, unsigned long long& n_cross, unsigned long long (&n_wrap)[6],
-                                             float* sacc = nullptr, unsigned* shist = nullptr, WarpTail* tail = nullptr) {
+                                             float* sacc = nullptr, unsigned* shist = nullptr) {
     const int m = first + lane;
     bool leaves = false;
     unsigned leaver = 0;
-    R fpx = 0, fpy = 0, fpz = 0;      // PLACE: final position and cell, placed warp-collectively below
-    int fc = -1;
     if (lane < count) {
         R px = ml.x[m], py = ml.y[m], pz = ml.z[m];
         R dx = ml.rx[m], dy = ml.ry[m], dz = ml.rz[m];
         const R qq = ml.q[m];
         int c = ml.cell[m];
-        const int c_in = c;
         for (;;) {
             R sx, sy, sz, mx, my, mz, v5, dirv;
             const int axis = mover_streak(px, py, pz, dx, dy, dz, qq, sx, sy, sz, mx, my, mz, v5, dirv);
             R jc[12];
             streak_currents<FMA>(qq, sx, sy, sz, mx, my, mz, v5, jc);
-            if (!CPIC_KO(64)) {
-                if constexpr (PRIV) {
-                    acc_add4<true>(nullptr, sacc, c, 0, (float)jc[0], (float)jc[1], (float)jc[2], (float)jc[3]);
-                    acc_add4<true>(nullptr, sacc, c, 1, (float)jc[4], (float)jc[5], (float)jc[6], (float)jc[7]);
-                    acc_add4<true>(nullptr, sacc, c, 2, (float)jc[8], (float)jc[9], (float)jc[10], (float)jc[11]);
-                } else if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)c * 12, jc);
-                else row_add_vec(a.acc + (long long)c * 12, jc);
-            } else if (jc[0] == R(-123.25)) a.acc[0] = jc[5];      // (keeps the arithmetic alive)
+            if constexpr (PRIV) {
+                acc_add4<true>(nullptr, sacc, c, 0, (float)jc[0], (float)jc[1], (float)jc[2], (float)jc[3]);
+                acc_add4<true>(nullptr, sacc, c, 1, (float)jc[4], (float)jc[5], (float)jc[6], (float)jc[7]);
+                acc_add4<true>(nullptr, sacc, c, 2, (float)jc[8], (float)jc[9], (float)jc[10], (float)jc[11]);
+            } else if constexpr (DEPOSIT == 1) row_add_scalar(a.acc + (long long)c * 12, jc);
+            else row_add_vec(a.acc + (long long)c * 12, jc);
             if (axis == 3) break;
             // snap onto the face, move to the neighbour, re-enter from its other side
             const int code = cross_face(c, axis, dirv, a);
@@ -430,15 +376,9 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
             }
         }
         const long long pn = ml.idx[m];
-        (void)c_in;
         leaves = a.leave_list && (c < a.leave_lo || c >= a.leave_hi);
         leaver = (unsigned)pn;
-        if (CPIC_KO(128)) {
-            if (px == R(-123.25)) a.dst.store_pos(pn, px, py, pz, c);
-        } else if constexpr (PLACE) {
-            fpx = px; fpy = py; fpz = pz; fc = c;
-            hist_add<PRIV>(a.hist, shist, c, 1u);
-        } else if constexpr (OUTOFPLACE) {
+        if constexpr (OUTOFPLACE) {
             a.dst.store_pos(pn, px, py, pz, c);
             hist_add<PRIV>(a.hist, shist, c, 1u);
         } else {
@@ -447,23 +387,6 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
         }
     }
     __syncwarp();
-    if constexpr (PLACE) {
-        // the final cells are known: every mover claims a slot of ITS segment (overflow: the warp's tail chunk) and
-        // its whole record is written once
-        const bool have = fc >= 0;
-        unsigned slot = 0;
-        if (have) slot = atomicAdd(a.cursor + fc, 1u);
-        const bool ov = have && slot >= a.seg_start[fc + 1];
-        const unsigned ts = warp_tail_slot(*tail, ov, a, lane);
-        if (ov) slot = ts;
-        if (have && slot < a.dst_cap) {
-            PRec<R> o;
-            o.pos.x = fpx; o.pos.y = fpy; o.pos.z = fpz; o.pos.w = cell_to_real(fc, R(0));
-            o.mom.x = ml.ux[m]; o.mom.y = ml.uy[m]; o.mom.z = ml.uz[m]; o.mom.w = ml.w[m];
-            a.dst.rec[slot] = o;
-        }
-        leaver = slot;
-    }
     if (a.leave_list) {      // slab mode: list the particles left in a z ghost plane, one counter atomic per warp
         const unsigned lm = __ballot_sync(0xffffffffu, leaves);
         if (lm) {

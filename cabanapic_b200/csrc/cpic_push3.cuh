@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
     __syncthreads();
     unsigned phase = 0;
     // work items: chunks [0, nchunks) of q.ch cells each, then tail items of 64*PUSH3_WARPS*8 particles behind the segments
+    if (a.np_dev && a.np_dev[1]) return;      // a migration flagged an overflow / inconsistency (reported by sync_np)
     const unsigned np_ = (unsigned)(a.np_dev ? *a.np_dev : a.np);
     const unsigned tail_lo = q.sin[q.nc];      // particles [tail_lo, np) lie behind the segments (slab mode: arrivals of a migration)
     const unsigned tail_n = np_ > tail_lo ? np_ - tail_lo : 0u;

@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(256) k_hist_add(const int* __restrict__ cell, 
 // bsum for the next level.
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = 256 * SCAN_ITEMS;
-__global__ void __launch_bounds__(256) k_scan_tile(const unsigned* __restrict__ in, unsigned* __restrict__ out,
-                                                   long long n, unsigned* __restrict__ bsum) {
+// (in and out may alias -- every launch is in place -- so neither is __restrict__)
+__global__ void __launch_bounds__(256) k_scan_tile(const unsigned* in, unsigned* out, long long n, unsigned* bsum) {
     __shared__ unsigned warp_tot[8];
     const long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     unsigned v[SCAN_ITEMS], run = 0;
@@ -91,8 +91,7 @@ __global__ void __launch_bounds__(256) k_scan_tile(const unsigned* __restrict__ 
     }
     if (threadIdx.x == 255 && bsum) bsum[blockIdx.x] = woff + inc;
 }
-__global__ void __launch_bounds__(256) k_scan_add(unsigned* __restrict__ out, long long n,
-                                                  const unsigned* __restrict__ boff) {
+__global__ void __launch_bounds__(256) k_scan_add(unsigned* out, long long n, const unsigned* boff) {
     const long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     const unsigned add = boff[blockIdx.x];
 #pragma unroll
@@ -120,52 +119,6 @@ __global__ void __launch_bounds__(256) k_sort_scatter(Particles<R> src, Particle
     base = __shfl_sync(0xffffffffu, base, head_lane);
     if (!valid) return;
     dst.rec[(long long)base + rank] = r;
-}
-
-// ---- PUSH2_PLACE (experimental, cpic_push2.cuh): helpers of the placement by new cell ---------------------------
-// segment capacities: the known counts rounded up to even, so that a lane's pair never straddles two cells
-__global__ void __launch_bounds__(256) k_even_caps(unsigned* __restrict__ count, long long nc) {
-    const long long c = blockIdx.x * 256LL + threadIdx.x;
-    if (c < nc) count[c] = (count[c] + 1u) & ~1u;
-    else if (c == nc) count[c] = 0u;          // sentinel: its scan value is the start of the overflow tail
-}
-// after a placing push: the slots of a segment that nobody claimed become holes (cell -1); thread 0 publishes the
-// extent of the store (segments + overflow tail) and flags a capacity overflow.  info: [0] extent [1] error
-template <class R>
-__global__ void __launch_bounds__(256) k_place_finish(Particles<R> dst, const unsigned* __restrict__ cursor,
-                                                      const unsigned* __restrict__ seg_start, long long nc,
-                                                      const unsigned* __restrict__ over, long long cap, long long* __restrict__ info) {
-    const long long c = blockIdx.x * 256LL + threadIdx.x;
-    if (c == 0) {
-        const long long ext = (long long)seg_start[nc] + *over;
-        info[0] = ext > cap ? cap : ext;
-        if (ext > cap) info[1] |= 1;
-    }
-    if (c >= nc) return;
-    const unsigned end = seg_start[c + 1];
-    unsigned s = cursor[c];
-    if (s < seg_start[c]) s = seg_start[c];
-    for (; s < end; ++s) dst.rec[s].pos.w = cell_to_real(-1, R(0));
-}
-// counting-sort scatter over a store with holes and a device-side extent: back to a dense, cell-ordered store
-template <class R>
-__global__ void __launch_bounds__(256) k_sort_scatter_ext(Particles<R> src, Particles<R> dst, const long long* __restrict__ extent,
-                                                          unsigned* __restrict__ cursor) {
-    const long long np = *extent;
-    const int lane = threadIdx.x & 31;
-    for (long long base = blockIdx.x * 256LL + (threadIdx.x & ~31); base < np; base += gridDim.x * 256LL) {
-        const long long n = base + lane;
-        bool valid = n < np;
-        int c = -1 - lane;
-        PRec<R> r;
-        if (valid) { r = src.rec[n]; c = real_to_cell(r.pos.w); if (c < 0) { valid = false; c = -1 - lane; } }
-        int rank, head_lane;
-        const int len = run_length_at_head(c, lane, rank, head_lane);
-        unsigned b = 0;
-        if (len > 0 && valid) b = atomicAdd(cursor + c, (unsigned)len);
-        b = __shfl_sync(0xffffffffu, b, head_lane);
-        if (valid) dst.rec[(long long)b + rank] = r;
-    }
 }
 
 }  // namespace cpic

@@ -677,7 +677,139 @@ class ReplicatedBench(_BenchRunner):
         return f"grid replicated on {self.world} GPUs, particles split, NCCL all-reduce of the accumulator"
 
 
-def make_runner(d, k, we, rank, world, local, mode="auto", fp_mode=_lib.FP_STRICT):
+class NativeBench:
+    """bench.py runner over the NATIVE multi-GPU layer (include/cabanapic_b200_mgpu.h): the whole step -- kernels, plane
+    exchange, particle migration, NCCL calls, CUDA-graph replay -- is host C++ inside the library; torch.distributed
+    only hands the 128-byte NCCL id to the ranks and reduces the timings."""
+
+    def __init__(self, d, k, we, rank, world, local, fp_mode, mode):
+        self.d, self.k, self.we, self.rank, self.world, self.local, self.fp, self.mode = d, k, we, rank, world, local, fp_mode, mode
+        self.l0 = 0
+        self.t_ms = 0.0
+        self.host_ms = 0.0
+        self.used_graph = False
+        self.use_graph = True
+        self._profile = False
+        self._push_ms = 0.0
+
+    def setup(self):
+        import os
+        d = self.d
+        dev = torch.device("cuda", self.local)
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if self.rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(_lib.Mgpu.unique_id()), dtype=torch.uint8))
+        if self.world > 1:
+            dist.broadcast(idt, 0)
+        uid = bytes(idt.cpu().numpy().tobytes())
+        per_plane = d.nx * d.ny * d.nppc
+        if self.mode == "slab":
+            nzl = slab_ranges(d.nz, self.world)[self.rank][1]
+            cap = int(per_plane * nzl * 1.10) + 4096
+            send_cap = max(4096, int(per_plane * 0.05))
+            mode = _lib.MGPU_SLAB
+        else:
+            n = d.num_particles
+            cap = n * (self.rank + 1) // self.world - n * self.rank // self.world
+            send_cap, mode = 0, _lib.MGPU_REPLICATED
+        self.use_graph = not os.environ.get("CPIC_NO_GRAPH")
+        self.m = _lib.Mgpu(d.nx, d.ny, d.nz, self.rank, self.world, uid, mode=mode, max_particles=cap, real=d.real,
+                           device=self.local, fp_mode=self.fp, send_capacity=send_cap)
+        self.m.init_uniform_plasma(d.nppc, weight=self.we)
+        self.m.sync()
+
+    def step(self, n, sort_interval):
+        c = self.m.ctx
+        self.l0 = c.launch_count
+        t0 = time.perf_counter()
+        self.m.step(self.k, n, sort_interval, use_graph=self.use_graph)
+        self.host_ms = (time.perf_counter() - t0) * 1e3
+        self.m.sync()
+        self.used_graph = self.used_graph or self.m.used_graph
+        self.t_ms = c.last_ms(3)
+        if self._profile:
+            self._push_ms += c.last_ms(0) * n          # no per-step sync: the last push of the call stands for all of them
+
+    def prepare_timed(self, sort_interval):
+        pass                                            # (the library captures its graph on the first eligible call)
+
+    def profile(self, on):
+        self._profile = bool(on)
+        self._push_ms = 0.0
+
+    def profile_result(self):
+        return {"push_ms": self._push_ms, "steps": 0, "push_timing": "device time of the last push of the timed call x steps"}
+
+    def device_ms(self):
+        return self.t_ms
+
+    def launches_in_timed_region(self):
+        return self.m.ctx.launch_count - self.l0
+
+    def local_particles(self):
+        return self.m.ctx.num_particles
+
+    def digest(self):
+        return self.m.state_digest()
+
+    def describe(self):
+        how = "two steps per CUDA-graph replay" if self.used_graph else "eager launches"
+        if self.mode == "slab":
+            return (f"{self.world} z-slabs, native C++ stepper (cpic_mgpu_step): NCCL ghost-plane exchange + device-counted "
+                    f"particle migration, {how}")
+        return f"grid replicated on {self.world} GPUs, particles split, ncclAllReduce of the accumulator (cpic_mgpu_step)"
+
+    def e2e(self, steps, sort_interval):
+        """Per step: H2D of this rank's particles + fields from pinned host memory, one step with all exchanges, D2H of
+        particles + fields (every rank, concurrently)."""
+        import ctypes as C
+        import psutil
+        c = self.m.ctx
+        n = c.num_particles
+        nbytes = n * 32 + 9 * c.nc * 4
+        if psutil.virtual_memory().available < 1.6 * nbytes * self.world:
+            return None
+        names = "dx dy dz ux uy uz w".split()
+        host = {m: torch.empty(n, dtype=torch.float32, pin_memory=True).numpy() for m in names}
+        host["cell"] = torch.empty(n, dtype=torch.int32, pin_memory=True).numpy()
+        cap2 = int(n * 1.05) + 1024                       # the count drifts by the net migration
+        back = {m: torch.empty(cap2, dtype=torch.float32, pin_memory=True).numpy() for m in names}
+        back["cell"] = torch.empty(cap2, dtype=torch.int32, pin_memory=True).numpy()
+        hf = torch.empty((9, c.nc), dtype=torch.float32, pin_memory=True).numpy()
+        L = c.L
+        up = [host[m].ctypes.data_as(C.c_void_p) for m in names] + [host["cell"].ctypes.data_as(C.c_void_p)]
+        dn = [back[m].ctypes.data_as(C.c_void_p) for m in names] + [back["cell"].ctypes.data_as(C.c_void_p)]
+        fptr = (C.c_void_p * 9)(*[hf[m].ctypes.data for m in range(9)])
+        got = C.c_int64()
+        c._ck(L.cpic_download_particles(c.h, *up, n, C.byref(got)))
+        c._ck(L.cpic_download_fields(c.h, fptr))
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            c._ck(L.cpic_upload_particles(c.h, *up, n))
+            c._ck(L.cpic_upload_fields(c.h, fptr))
+            self.m.step(self.k, 1, sort_interval, use_graph=False)
+            c._ck(L.cpic_download_particles(c.h, *dn, cap2, C.byref(got)))
+            c._ck(L.cpic_download_fields(c.h, fptr))
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        return {"value": self.d.num_particles * steps / sec, "unit": "particle-steps/s",
+                "h2d_bytes_per_step": nbytes * self.world, "d2h_bytes_per_step": nbytes * self.world,
+                "steps": steps, "seconds": sec,
+                "what": "per step and rank: H2D local particles+fields from pinned host, one cpic_mgpu_step incl. NCCL "
+                        "exchanges, D2H local particles+fields; bytes summed over ranks"}
+
+    def close(self):
+        self.m.close()
+
+
+def make_runner(d, k, we, rank, world, local, mode="auto", fp_mode=_lib.FP_STRICT, native=True):
     mode = choose_mode(d.nx, d.ny, d.nz, world, mode)
+    if native and np.dtype(d.real).itemsize == 4:
+        return NativeBench(d, k, we, rank, world, local, fp_mode, mode)
     cls = SlabBench if mode == "slab" else ReplicatedBench
     return cls(d, k, we, rank, world, local, fp_mode)

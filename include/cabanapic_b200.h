@@ -136,6 +136,11 @@ int  cpic_energies(cpic_ctx* ctx, double* e_energy, double* b_energy);   /* src/
  * cpic_energies it closes the energy budget: w_p (gamma-1) m c^2 + (eps0/2) sum (E^2 + cB^2) dV is conserved by
  * the scheme up to grid heating, a size-independent check of the whole loop. */
 int  cpic_kinetic_energy(cpic_ctx* ctx, double* out);
+/* One-pass digest of the particle store + the field energies (bench / multi-GPU parity block): out[0] particles,
+ * [1] sum of weights, [2] particles whose cell is not an interior voxel, [3] particles with an offset outside [-1,1],
+ * [4] kinetic energy (as cpic_kinetic_energy), [5] E energy, [6] B energy (as cpic_energies), [7] 0 (reserved: particles
+ * migrated, see cpic_mgpu_state_digest). */
+int  cpic_state_digest(cpic_ctx* ctx, double out[8]);
 int  cpic_update_ghosts(cpic_ctx* ctx, int which /* 0: fold J, 1: copy J, 2: copy cB, 3 / 4: first / second sweep of the J fold only */); /* src/fields.h:11-271 */
 
 /* n whole steps in the reference's order (example/example.cpp:221-266), fused on the

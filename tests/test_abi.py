@@ -10,8 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "cabanapic_b200.h")).read()
+def declared_functions(header="cabanapic_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(cpic_[a-z0-9_]+)\s*\(", src)))
 
@@ -25,6 +25,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} declared in the header but not exported"
     assert sorted(m._lib.EXPORTED) == names, "python binding list and header disagree"
     assert L.cpic_abi_version() == 1
+    # the multi-GPU layer (host C++ + NCCL inside the same library)
+    mg = declared_functions("cabanapic_b200_mgpu.h")
+    assert len(mg) >= 14
+    for n in mg:
+        assert hasattr(L, n), f"{n} declared in cabanapic_b200_mgpu.h but not exported"
+    assert sorted(m._lib.EXPORTED_MGPU) == mg
 
 
 def test_struct_layouts_match_header():
