@@ -134,6 +134,8 @@ def lib() -> C.CDLL:
             "cpic_enable_step_profile": [vp, i32],
             "cpic_step_profile": [vp, C.POINTER(dbl), C.POINTER(i64)],
             "cpic_state_digest": [vp, C.POINTER(dbl)],
+            "cpic_create_species": [vp, i64, C.POINTER(vp)],
+            "cpic_step_species": [vp, C.POINTER(vp), C.POINTER(Consts), i32, i64, i32, vp],
             # multi-GPU layer (include/cabanapic_b200_mgpu.h)
             "cpic_mgpu_unique_id": [vp],
             "cpic_mgpu_bootstrap_file": [C.c_char_p, i32, i32, dbl, vp],
@@ -142,6 +144,7 @@ def lib() -> C.CDLL:
             "cpic_mgpu_init_uniform_plasma": [vp, i32, C.c_uint64, dbl, dbl, dbl, dbl],
             "cpic_mgpu_reduce_accumulator": [vp],
             "cpic_mgpu_step": [vp, C.POINTER(Consts), i64, i32, i32],
+            "cpic_mgpu_prepare_graph": [vp, C.POINTER(Consts)],
             "cpic_mgpu_migration_counts": [vp, C.POINTER(i64)],
             "cpic_mgpu_last_migration": [vp, C.POINTER(i64)],
             "cpic_mgpu_energies": [vp, C.POINTER(dbl), C.POINTER(dbl)],
@@ -172,10 +175,11 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
             "cpic_energies", "cpic_kinetic_energy", "cpic_update_ghosts", "cpic_step", "cpic_step_host", "cpic_sort_particles", "cpic_push_reorder", "cpic_init_uniform_plasma", "cpic_enable_push_stats",
             "cpic_push_stats_get", "cpic_device_ptr", "cpic_set_stream", "cpic_set_num_particles", "cpic_set_modes",
             "cpic_set_axis_periodic", "cpic_advance_b_stencil", "cpic_advance_e_stencil", "cpic_extract_z_leavers", "cpic_append_particles_device", "cpic_slab_extract_async", "cpic_slab_append_async",
-            "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile", "cpic_state_digest"]
+            "cpic_last_ms", "cpic_launch_count", "cpic_enable_step_profile", "cpic_step_profile", "cpic_state_digest",
+            "cpic_create_species", "cpic_step_species"]
 EXPORTED_MGPU = ["cpic_mgpu_last_error", "cpic_mgpu_unique_id", "cpic_mgpu_bootstrap_file", "cpic_mgpu_create",
                  "cpic_mgpu_destroy", "cpic_mgpu_context", "cpic_mgpu_layout", "cpic_mgpu_init_uniform_plasma",
-                 "cpic_mgpu_reduce_accumulator", "cpic_mgpu_step", "cpic_mgpu_migration_counts", "cpic_mgpu_last_migration",
+                 "cpic_mgpu_reduce_accumulator", "cpic_mgpu_step", "cpic_mgpu_prepare_graph", "cpic_mgpu_migration_counts", "cpic_mgpu_last_migration",
                  "cpic_mgpu_energies", "cpic_mgpu_state_digest", "cpic_mgpu_sync", "cpic_mgpu_used_graph"]
 MGPU_REPLICATED, MGPU_SLAB, MGPU_AUTO = 0, 1, 2
 DIGEST_NAMES = ["particles", "weight_sum", "cells_not_interior", "offsets_out_of_range", "kinetic_energy",
@@ -233,6 +237,23 @@ class Context:
         d = (C.c_double * 8)()
         self._ck(self.L.cpic_state_digest(self.h, d))
         return dict(zip(DIGEST_NAMES, list(d)))
+
+    def create_species(self, max_particles):
+        """another particle store (species) on this context's fields / accumulators; close it before this context"""
+        h = C.c_void_p()
+        self._ck(self.L.cpic_create_species(self.h, int(max_particles), C.byref(h)))
+        sp = Context.borrowed(h.value, self.nx, self.ny, self.nz, self.real, self.solver)
+        sp._borrowed = False          # owned: cpic_destroy frees only what the species itself allocated
+        sp._parent = self
+        return sp
+
+    def step_species(self, species, consts, nsteps=1, sort_interval=0, energies=False):
+        n = len(species)
+        hs = (C.c_void_p * n)(*[s.h.value if isinstance(s.h, C.c_void_p) else s.h for s in species])
+        ks = (Consts * n)(*consts)
+        en = np.zeros((nsteps, 2), dtype=np.float64) if energies else None
+        self._ck(self.L.cpic_step_species(self.h, hs, ks, n, nsteps, sort_interval, _p(en)))
+        return en
 
     def __del__(self):
         try:
@@ -502,6 +523,10 @@ class Mgpu:
 
     def step(self, k: Consts, nsteps=1, sort_interval=SORT_FUSED, use_graph=False):
         self._ck(self.L.cpic_mgpu_step(self.h, C.byref(k), nsteps, sort_interval, 1 if use_graph else 0))
+
+    def prepare_graph(self, k: Consts):
+        """capture the pair-of-steps graph now (nothing executes); False when the graph path does not apply"""
+        return self.L.cpic_mgpu_prepare_graph(self.h, C.byref(k)) == 0
 
     def reduce_accumulator(self):
         self._ck(self.L.cpic_mgpu_reduce_accumulator(self.h))

@@ -105,6 +105,7 @@ struct CtxBase {
     virtual int slab_extract_async(void* lo, void* hi, long long cap, long long* counts_dev, int rebase_lo, int rebase_hi) = 0;
     virtual int slab_append_async(const void* buf, long long cap, const long long* count_dev) = 0;
     virtual bool few_cells() const = 0;   // grid small enough for the block-private accumulator (k_push2<PRIV>)
+    virtual bool is_species_of(const CtxBase* p) const = 0;
     virtual int sync_np() = 0;      // device-count mode -> host-count mode (synchronises); no-op otherwise
     long long fb_steps = 0;         // steps taken in the few-cells fallback of CPIC_SORT_FUSED (sort when % 8 == 0)
     bool dev_count = false;         // slab mode: np lives in dc[0] on the device, the host's np is stale
@@ -139,14 +140,18 @@ struct Ctx final : CtxBase {
     unsigned* scan_l2 = nullptr;
     long long n_l1 = 0, n_l2 = 0;
     unsigned* bad = nullptr;
-    double* en_dev = nullptr;          // 2 doubles scratch
+    // A SPECIES context (cpic_create_species): its own particle store, sort state and step constants, but the field,
+    // interpolator and accumulator arrays and the stream of its parent -- every push deposits into the same J.
+    Ctx<R>* parent = nullptr;
+    double* en_dev = nullptr;          // 8 doubles scratch
     unsigned long long* stats = nullptr;  // 8 counters
 
     ~Ctx() override {
         if (stream || true) {
             cudaSetDevice(prm.device);
             for (auto& e : ev) if (e) cudaEventDestroy(e);
-            cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer); cudaFree(fields); cudaFree(interp); cudaFree(acc);
+            cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer);
+            if (!parent) { cudaFree(fields); cudaFree(interp); cudaFree(acc); }
             cudaFree(seg[0]); cudaFree(seg[1]); cudaFree(cursor3); cudaFree(work3); cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count); cudaFree(dc);
             for (auto b : hs_buf) cudaFree(b);
             for (auto e : hs_ev) if (e) cudaEventDestroy(e);
@@ -171,8 +176,11 @@ struct Ctx final : CtxBase {
     int init() {
         int rc;
         if ((rc = cuda(cudaSetDevice(prm.device), "cudaSetDevice"))) return rc;
-        if ((rc = cuda(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return rc;
-        own_stream = true;
+        if (parent) { stream = parent->stream; own_stream = false; }
+        else {
+            if ((rc = cuda(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return rc;
+            own_stream = true;
+        }
         for (auto& e : ev)
             if ((rc = cuda(cudaEventCreate(&e), "cudaEventCreate"))) return rc;
         // developer tuning knobs (not part of the ABI)
@@ -191,9 +199,12 @@ struct Ctx final : CtxBase {
             if ((rc = cuda(cudaMalloc(&pbuf[b], pbytes), "cudaMalloc(particles)"))) return rc;
             P[b].rec = reinterpret_cast<PRec<R>*>(pbuf[b]);
         }
-        if ((rc = cuda(cudaMalloc(&fields, (size_t)nc_pad * F_N * sizeof(R)), "cudaMalloc(fields)"))) return rc;
-        if ((rc = cuda(cudaMalloc(&interp, (size_t)g.nc * S * sizeof(R)), "cudaMalloc(interpolators)"))) return rc;
-        if ((rc = cuda(cudaMalloc(&acc, (size_t)g.nc * 12 * sizeof(R)), "cudaMalloc(accumulators)"))) return rc;
+        if (parent) { fields = parent->fields; interp = parent->interp; acc = parent->acc; }
+        else {
+            if ((rc = cuda(cudaMalloc(&fields, (size_t)nc_pad * F_N * sizeof(R)), "cudaMalloc(fields)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&interp, (size_t)g.nc * S * sizeof(R)), "cudaMalloc(interpolators)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&acc, (size_t)g.nc * 12 * sizeof(R)), "cudaMalloc(accumulators)"))) return rc;
+        }
         if ((rc = cuda(cudaMalloc(&bad, sizeof(unsigned)), "cudaMalloc"))) return rc;
         if ((rc = cuda(cudaMalloc(&en_dev, 8 * sizeof(double)), "cudaMalloc"))) return rc;
         if ((rc = cuda(cudaMalloc(&stats, 8 * sizeof(unsigned long long)), "cudaMalloc"))) return rc;
@@ -209,9 +220,11 @@ struct Ctx final : CtxBase {
         // Field_Solver ctor zeroes the fields (src/fields.h:279-315); interpolators are zeroed by
         // initialize_interpolator (src/interpolator.cpp:125-172); Kokkos::View zero-initialises.
         if ((rc = init_push3())) return rc;
-        cudaMemsetAsync(fields, 0, (size_t)nc_pad * F_N * sizeof(R), stream);
-        cudaMemsetAsync(interp, 0, (size_t)g.nc * S * sizeof(R), stream);
-        cudaMemsetAsync(acc, 0, (size_t)g.nc * 12 * sizeof(R), stream);
+        if (!parent) {
+            cudaMemsetAsync(fields, 0, (size_t)nc_pad * F_N * sizeof(R), stream);
+            cudaMemsetAsync(interp, 0, (size_t)g.nc * S * sizeof(R), stream);
+            cudaMemsetAsync(acc, 0, (size_t)g.nc * 12 * sizeof(R), stream);
+        }
         cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
         return cuda(cudaStreamSynchronize(stream), "init");
     }
@@ -313,7 +326,7 @@ struct Ctx final : CtxBase {
     }
     int ghost_copy(int m0) {
         Fields<R> f = F();
-        k_ghost_copy3<R><<<blocks_for(g.nc), 256, 0, stream>>>(f.c[m0], f.c[m0 + 1], f.c[m0 + 2], g);
+        k_ghost_copy3<R><<<blocks_for(ghost_cell_count(g)), 256, 0, stream>>>(f.c[m0], f.c[m0 + 1], f.c[m0 + 2], g);
         return check_launch("k_ghost_copy3");
     }
     int ghost_fold() {
@@ -513,6 +526,7 @@ struct Ctx final : CtxBase {
         return check_launch("k_append_finish_dev");
     }
     int update_ghosts(int which) override {
+        if (reflecting()) return CPIC_OK;      // no periodic images
         if (which == 0) return ghost_fold();
         if (which == 3) return fold_phase(0);
         if (which == 4) return fold_phase(1);
@@ -540,11 +554,19 @@ struct Ctx final : CtxBase {
         Box b{1, 1, 1, g.nx, g.ny, g.nz};
         k_advance_b<R><<<blocks_for(b.count()), 256, 0, stream>>>(F(), g, b, (R)px, (R)py, (R)pz);
         int rc = check_launch("k_advance_b");
-        if (rc) return rc;
+        if (rc || reflecting()) return rc;      // (conducting walls: the normal cB on a wall never changes, nothing to copy)
         return ghost_copy(F_CBX);   // src/fields.h:718
     }
+    bool reflecting() const { return prm.boundary == CPIC_BOUNDARY_REFLECT; }
     int advance_e(double px, double py, double pz, double dt_eps0) override {
-        int rc = ghost_fold();                                   // src/fields.h:642 / :530
+        int rc;
+        if (reflecting()) {      // conducting walls: no periodic fold / copy; stencil, then E_tang = 0 on the walls
+            if ((rc = stencil_only(1, px, py, pz, dt_eps0))) return rc;
+            Fields<R> f = F();
+            k_pec_walls<R><<<blocks_for(g.nc), 256, 0, stream>>>(f.c[F_EX], f.c[F_EY], f.c[F_EZ], g);
+            return check_launch("k_pec_walls");
+        }
+        rc = ghost_fold();                                       // src/fields.h:642 / :530
         if (rc) return rc;
         if (prm.solver == CPIC_SOLVER_ES_1D) {
             k_advance_e_es<R><<<blocks_for(g.nc), 256, 0, stream>>>(F(), g.nc, (R)dt_eps0);
@@ -619,6 +641,7 @@ struct Ctx final : CtxBase {
     bool push2_priv = true;
     bool use_priv() const { return push2_priv && g.nc <= PRIV_MAX_CELLS; }
     bool few_cells() const override { return use_priv() && can_reorder(); }
+    bool is_species_of(const CtxBase* p) const override { return parent != nullptr && static_cast<const CtxBase*>(parent) == p; }
     template <bool FMA, bool ST, bool FD>
     int launch_push2(const PushArgs<float>& a) {
         if (!ST && a.priv_nc > 0) return a.hist ? launch_push2h<FMA, ST, FD, true, false, true>(a) : launch_push2h<FMA, ST, FD, false, false, true>(a);
@@ -837,6 +860,7 @@ struct Ctx final : CtxBase {
         a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.ng = g.ng; a.gx = g.gx; a.gy = g.gy;
         a.magic_gx = (unsigned)(((1ull << 32) + g.gx - 1) / g.gx); a.magic_gy = (unsigned)(((1ull << 32) + g.gy - 1) / g.gy);
         a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC ? g.per : 0;
+        a.reflect = reflecting() ? 7 : 0;
         a.stats = stats;
         a.hist = nullptr;
         a.dst = P[cur]; a.cursor = nullptr;
@@ -856,6 +880,7 @@ struct Ctx final : CtxBase {
         a.nx = g.nx; a.ny = g.ny; a.nz = g.nz; a.ng = g.ng; a.gx = g.gx; a.gy = g.gy;
         a.magic_gx = (unsigned)(((1ull << 32) + g.gx - 1) / g.gx); a.magic_gy = (unsigned)(((1ull << 32) + g.gy - 1) / g.gy);
         a.periodic = prm.boundary == CPIC_BOUNDARY_PERIODIC ? g.per : 0;
+        a.reflect = reflecting() ? 7 : 0;
         a.stats = stats;
         a.hist = nullptr;
         hist_valid = false; cursor_valid = false; seg_valid = false;
@@ -1090,8 +1115,8 @@ int validate(const cpic_params& p, std::string& why) {
     if (p.real_bytes != 4 && p.real_bytes != 8) { why = "real_bytes must be 4 or 8"; return CPIC_E_INVALID; }
     if (p.solver != CPIC_SOLVER_EM && p.solver != CPIC_SOLVER_ES_1D) { why = "unknown solver"; return CPIC_E_INVALID; }
     if (p.solver == CPIC_SOLVER_ES_1D && (p.ny > 1 || p.nz > 1)) { why = "ES field solver supports 1D only (example/example.cpp:69-74)"; return CPIC_E_INVALID; }
-    if (p.boundary == CPIC_BOUNDARY_REFLECT) { why = "Boundary::Reflect is not implemented (the reference exits, src/fields.h:21-25,113-117)"; return CPIC_E_UNSUPPORTED; }
-    if (p.boundary != CPIC_BOUNDARY_PERIODIC) { why = "unknown boundary"; return CPIC_E_INVALID; }
+    if (p.boundary != CPIC_BOUNDARY_PERIODIC && p.boundary != CPIC_BOUNDARY_REFLECT) { why = "unknown boundary"; return CPIC_E_INVALID; }
+    if (p.boundary == CPIC_BOUNDARY_REFLECT && p.solver != CPIC_SOLVER_EM) { why = "Boundary::Reflect (reflecting particles + conducting walls) is implemented for the EM solver only"; return CPIC_E_UNSUPPORTED; }
     if (p.max_particles < 0 || p.max_particles > (1ll << 31) - 64) { why = "max_particles must be in [0, 2^31)"; return CPIC_E_INVALID; }
     const long long nc = (long long)(p.nx + 2) * (p.ny + 2) * (p.nz + 2);
     if (nc > (1ll << 31) - 1) { snprintf(buf, sizeof buf, "%lld cells overflow the int cell index", nc); why = buf; return CPIC_E_INVALID; }
@@ -1140,6 +1165,84 @@ int cpic_create(const cpic_params* params, cpic_ctx** out) {
     if (rc) { g_create_error = c->err; delete c; return rc; }
     *out = reinterpret_cast<cpic_ctx*>(c);
     return CPIC_OK;
+}
+
+int cpic_create_species(cpic_ctx* parent, int64_t max_particles, cpic_ctx** out) {
+    CTX_OR_FAIL(parent);
+    if (!out || max_particles < 0 || max_particles > (1ll << 31) - 64) return c->fail(CPIC_E_INVALID, "create_species: bad arguments");
+    *out = nullptr;
+    int rc;
+    CtxBase* sp;
+    if (c->prm.real_bytes == 4) {
+        auto* ch = new Ctx<float>();
+        ch->parent = static_cast<Ctx<float>*>(c);
+        if (ch->parent->parent) { delete ch; return c->fail(CPIC_E_INVALID, "create_species: the parent must be a context of cpic_create"); }
+        ch->prm = c->prm; ch->prm.max_particles = max_particles; ch->g = c->g;
+        rc = ch->init();
+        sp = ch;
+    } else {
+        auto* ch = new Ctx<double>();
+        ch->parent = static_cast<Ctx<double>*>(c);
+        if (ch->parent->parent) { delete ch; return c->fail(CPIC_E_INVALID, "create_species: the parent must be a context of cpic_create"); }
+        ch->prm = c->prm; ch->prm.max_particles = max_particles; ch->g = c->g;
+        rc = ch->init();
+        sp = ch;
+    }
+    if (rc) { c->err = sp->err; delete sp; return rc; }
+    *out = reinterpret_cast<cpic_ctx*>(sp);
+    return CPIC_OK;
+}
+
+int cpic_step_species(cpic_ctx* ctx, cpic_ctx* const* species, const cpic_consts* consts, int32_t nspecies, int64_t nsteps,
+                      int32_t sort_interval, double* energies) {
+    CTX_OR_FAIL(ctx);
+    if (!species || !consts || nspecies < 1 || nsteps < 0 || sort_interval < CPIC_SORT_FUSED) return c->fail(CPIC_E_INVALID, "step_species: bad arguments");
+    for (int s = 0; s < nspecies; ++s) {
+        if (!species[s]) return c->fail(CPIC_E_INVALID, "step_species: null species");
+        CtxBase* sp = reinterpret_cast<CtxBase*>(species[s]);
+        if (sp != c && !sp->is_species_of(c)) return c->fail(CPIC_E_INVALID, "step_species: species %d does not belong to this context", s);
+        int rc = sp->sync_np();
+        if (rc) { c->err = sp->err; return rc; }
+    }
+    int rc = CPIC_OK;
+    double* en = nullptr;
+    if (energies && nsteps > 0)
+        if ((rc = c->cuda(cudaMalloc(&en, (size_t)nsteps * 2 * sizeof(double)), "cudaMalloc(energies)"))) return rc;
+    const cpic_consts* k = &consts[0];      // the field constants (dt, dx, px, dt_eps0 ...) are common to all species
+    const double hx = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->px) : 0.5 * k->px;
+    const double hy = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->py) : 0.5 * k->py;
+    const double hz = (c->prm.real_bytes == 4) ? (double)(0.5f * (float)k->pz) : 0.5 * k->pz;
+    c->rec(6);
+    for (int64_t st = 0; st < nsteps && !rc; ++st) {
+        // example/example.cpp:221-266 with the push repeated per species between clear and unload (the two-species form
+        // of the VPIC decks, decks/vpic/2stream-em0.cxx:207-208: every species deposits into the same accumulator)
+        rc = c->load_interpolator();
+        if (!rc) rc = c->clear_accumulator();
+        for (int s = 0; s < nspecies && !rc; ++s) {
+            CtxBase* sp = reinterpret_cast<CtxBase*>(species[s]);
+            const bool fused = sort_interval == CPIC_SORT_FUSED && !sp->few_cells();
+            if (!fused && sort_interval > 0 && st % sort_interval == 0) rc = sp->sort();
+            if (!rc) rc = fused ? sp->push_reorder(consts[s]) : sp->push(consts[s]);
+            if (rc) c->err = sp->err;
+        }
+        if (!rc) rc = c->unload_accumulator(*k);
+        if (!rc) rc = c->advance_b(hx, hy, hz);
+        if (!rc) rc = c->advance_e(k->px, k->py, k->pz, k->dt_eps0);
+        if (!rc) rc = c->advance_b(hx, hy, hz);
+        if (!rc && en) rc = c->energies_async(en + 2 * st);
+    }
+    c->rec(7);
+    c->ev_valid[3] = true;
+    if (!rc && en) {
+        rc = c->cuda(cudaMemcpyAsync(energies, en, (size_t)nsteps * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream), "D2H energies");
+        if (!rc) rc = c->cuda(cudaStreamSynchronize(c->stream), "step_species");
+        for (int64_t st = 0; st < nsteps && !rc; ++st) {
+            energies[2 * st] *= 0.5;
+            energies[2 * st + 1] = (c->prm.solver == CPIC_SOLVER_EM) ? 0.5 * energies[2 * st + 1] : 0.0;
+        }
+    }
+    if (en) { cudaStreamSynchronize(c->stream); cudaFree(en); }
+    return rc;
 }
 
 void cpic_destroy(cpic_ctx* ctx) {

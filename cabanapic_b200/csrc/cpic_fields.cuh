@@ -90,15 +90,38 @@ __global__ void __launch_bounds__(256) k_unload_accumulator(Fields<R> f, const R
 // y faces (incl. x ghosts) then z faces (incl. all).  The three ordered sweeps leave every
 // ghost cell equal to the interior cell at the wrapped coordinates, so one pass suffices:
 // each ghost thread reads interior(wrap(x),wrap(y),wrap(z)); interior cells are untouched.
+// One thread per GHOST cell (O(surface), not O(cells): at 256^3 the ghost layer is 2.3 % of the grid): the two z ghost
+// planes, then the y ghost rows of the interior planes, then the x ghost cells of the interior rows.
+inline long long ghost_cell_count(const Grid& g) {
+    return 2ll * g.gx * g.gy + 2ll * g.nz * g.gx + 2ll * g.nz * g.ny;
+}
 template <class R>
 __global__ void __launch_bounds__(256) k_ghost_copy3(R* __restrict__ a, R* __restrict__ b3, R* __restrict__ c,
                                                      Grid g) {
-    const long long t = blockIdx.x * 256LL + threadIdx.x;
-    if (t >= g.nc) return;
-    const long long row = t / g.gx;
-    const int x = (int)(t - row * g.gx);
-    const int z = (int)(row / g.gy);
-    const int y = (int)(row - (long long)z * g.gy);
+    long long t = blockIdx.x * 256LL + threadIdx.x;
+    const long long plane = (long long)g.gx * g.gy;
+    int x, y, z;
+    if (t < 2 * plane) {
+        z = t < plane ? 0 : g.nz + 1;
+        const long long r = t < plane ? t : t - plane;
+        y = (int)(r / g.gx); x = (int)(r - (long long)y * g.gx);
+    } else {
+        t -= 2 * plane;
+        const long long nrow = 2ll * g.nz * g.gx;
+        if (t < nrow) {
+            z = 1 + (int)(t / (2 * g.gx));
+            const int r = (int)(t % (2 * g.gx));
+            y = r < g.gx ? 0 : g.ny + 1;
+            x = r < g.gx ? r : r - g.gx;
+        } else {
+            t -= nrow;
+            if (t >= 2ll * g.nz * g.ny) return;
+            z = 1 + (int)(t / (2 * g.ny));
+            const int r = (int)(t % (2 * g.ny));
+            y = 1 + (r >> 1);
+            x = (r & 1) ? g.nx + 1 : 0;
+        }
+    }
     const int wx = (x == 0) ? g.nx : (x == g.nx + 1 ? 1 : x);
     const int wy = (y == 0) ? g.ny : (y == g.ny + 1 ? 1 : y);
     int wz = (z == 0) ? g.nz : (z == g.nz + 1 ? 1 : z);
@@ -106,9 +129,27 @@ __global__ void __launch_bounds__(256) k_ghost_copy3(R* __restrict__ a, R* __res
         if (wz != z) return;
         wz = z;
     }
-    if (wx == x && wy == y && wz == z) return;
+    const long long d = x + (long long)g.sy * y + (long long)g.sz * z;
     const long long s = wx + (long long)g.sy * wy + (long long)g.sz * wz;
-    a[t] = a[s]; b3[t] = b3[s]; c[t] = c[s];
+    a[d] = a[s]; b3[d] = b3[s]; c[d] = c[s];
+}
+
+// Field side of Boundary::Reflect (the reference exit(1)s, src/fields.h:21-25,113-117; parity unpinned): a perfectly
+// conducting box -- "anti_symmetric_fields: E_tang = 0", src/grid.h:4-17.  The walls are the node planes 1 and n+1 of
+// each axis; the E components tangential to a wall are zeroed after every E update.  One thread per cell of the six
+// wall planes would do; the box is small next to the particle work, so one thread per cell it is.
+template <class R>
+__global__ void __launch_bounds__(256) k_pec_walls(R* __restrict__ ex, R* __restrict__ ey, R* __restrict__ ez, Grid g) {
+    const long long t = blockIdx.x * 256LL + threadIdx.x;
+    if (t >= g.nc) return;
+    const long long row = t / g.gx;
+    const int x = (int)(t - row * g.gx);
+    const int z = (int)(row / g.gy);
+    const int y = (int)(row - (long long)z * g.gy);
+    const bool wx = x == 1 || x == g.nx + 1, wy = y == 1 || y == g.ny + 1, wz = z == 1 || z == g.nz + 1;
+    if (wy || wz) ex[t] = R(0);
+    if (wz || wx) ey[t] = R(0);
+    if (wx || wy) ez[t] = R(0);
 }
 
 // Reference: serial_update_ghosts, src/fields.h:126-183 -- periodic ghost FOLD of J.  Each

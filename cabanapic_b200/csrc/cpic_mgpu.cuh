@@ -360,6 +360,7 @@ int cpic_mgpu_create(const cpic_params* global, int32_t rank, int32_t world, con
         mode = (world > 1 && global->nz >= 2 * world && nc >= (1ll << 18)) ? CPIC_MGPU_SLAB : CPIC_MGPU_REPLICATED;
     }
     if (mode != CPIC_MGPU_SLAB && mode != CPIC_MGPU_REPLICATED) { g_mgpu_error = "mgpu_create: unknown mode"; return CPIC_E_INVALID; }
+    if (mode == CPIC_MGPU_SLAB && global->boundary != CPIC_BOUNDARY_PERIODIC) { g_mgpu_error = "mgpu_create: slab mode is periodic only"; return CPIC_E_UNSUPPORTED; }
     if (mode == CPIC_MGPU_SLAB) {
         if (global->real_bytes != 4 || global->solver != CPIC_SOLVER_EM || !global->enable_sort) { g_mgpu_error = "mgpu_create: slab mode needs float, the EM solver and enable_sort"; return CPIC_E_UNSUPPORTED; }
         if (global->nz < world) { g_mgpu_error = "mgpu_create: fewer z-planes than ranks"; return CPIC_E_INVALID; }
@@ -485,6 +486,19 @@ int cpic_mgpu_step(cpic_mgpu* mm, const cpic_consts* k, int64_t nsteps, int32_t 
         rc = m->replicated_step(*k, sort, fused);
     }
     m->steps_done += nsteps;
+    return rc;
+}
+
+int cpic_mgpu_prepare_graph(cpic_mgpu* mm, const cpic_consts* k) {
+    MGPU_OR_FAIL(mm);
+    if (!k) return m->fail(CPIC_E_INVALID, "prepare_graph: null consts");
+    CtxBase* c = m->c;
+    if (m->mode != CPIC_MGPU_SLAB || (c->g.per & 4) || m->graph_failed || m->steps_done < 2 || !c->dev_count || !c->seg_valid)
+        return m->fail(CPIC_E_UNSUPPORTED, "prepare_graph: needs slab mode after at least two eager fused steps");
+    if (m->gexec && same_consts(*k, m->graph_k)) return CPIC_OK;
+    if (m->gexec) { cudaGraphExecDestroy(m->gexec); m->gexec = nullptr; }
+    const int rc = m->capture_pair(*k);
+    if (rc) m->graph_failed = true;
     return rc;
 }
 

@@ -31,6 +31,7 @@ struct PushArgs {
     int nx, ny, nz, ng, gx, gy;
     unsigned magic_gx, magic_gy;   // ceil(2^32 / gx), ceil(2^32 / gy)
     int periodic;     // bit a: wrap along axis a (0 x, 1 y, 2 z); cleared: the particle stays in the ghost cell
+    int reflect;      // bit a: the domain faces of axis a reflect particles (Boundary::Reflect, src/move_p.h:298-324)
     int dep_thresh;   // mixed warps: runs at least this long are warp-reduced, shorter ones use direct atomics
     int dep_rounds;   // mixed warps: at most this many peel rounds before falling back to direct atomics
     unsigned long long* stats;  // optional: [0] movers [1] crossings [2..7] wraps per face
@@ -244,6 +245,10 @@ __device__ __forceinline__ int mover_streak(R& x, R& y, R& z, R& rx, R& ry, R& r
 // :9-54 (ghost-layer test, later tests override earlier, one ghost layer assumed),
 // :257-288 (periodic wrap), :351-352 (new voxel).  Returns the face code 0..5 (-x -y -z +x +y +z)
 // in the low bits and, if the neighbour was a ghost layer, 8 + that layer's code above them.
+// Boundary::Reflect (a.reflect; the reference keeps VPIC's block in comments, :298-324): when the face is a domain
+// face of a reflecting axis the particle keeps its cell and the CROSS_REFLECTED bit is set -- the caller then leaves the
+// position on the face and reverses the momentum component and the remaining displacement along that axis.
+constexpr int CROSS_REFLECTED = 8;
 template <class R>
 __device__ __forceinline__ int cross_face(int& ii, int axis, R dirv, const PushArgs<R>& a) {
     int face = axis;
@@ -262,6 +267,10 @@ __device__ __forceinline__ int cross_face(int& ii, int axis, R dirv, const PushA
     if (face == 3) ix++;
     if (face == 4) iy++;
     if (face == 5) iz++;
+    if (a.reflect & (1 << axis)) {
+        const int coord = axis == 0 ? ix : (axis == 1 ? iy : iz), top = axis == 0 ? a.nx : (axis == 1 ? a.ny : a.nz);
+        if (coord == 0 || coord == top + 1) return face | CROSS_REFLECTED;
+    }
     // detect_leaving_domain: later tests override earlier ones.  a.periodic is a per-axis mask
     // (7 = the reference); an axis whose bit is clear (slab mode: that ghost layer belongs to a
     // neighbour) neither wraps nor hides the wrap of another axis, so its tests are skipped.
@@ -353,6 +362,7 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
         R dx = ml.rx[m], dy = ml.ry[m], dz = ml.rz[m];
         const R qq = ml.q[m];
         int c = ml.cell[m];
+        unsigned flip = 0;
         for (;;) {
             R sx, sy, sz, mx, my, mz, v5, dirv;
             const int axis = mover_streak(px, py, pz, dx, dy, dz, qq, sx, sy, sz, mx, my, mz, v5, dirv);
@@ -367,15 +377,30 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
             if (axis == 3) break;
             // snap onto the face, move to the neighbour, re-enter from its other side
             const int code = cross_face(c, axis, dirv, a);
-            if (axis == 0) px = -dirv;
-            if (axis == 1) py = -dirv;
-            if (axis == 2) pz = -dirv;
+            if (code & CROSS_REFLECTED) {      // reflecting wall: stay on the face, turn around
+                if (axis == 0) { px = dirv; dx = -dx; }
+                if (axis == 1) { py = dirv; dy = -dy; }
+                if (axis == 2) { pz = dirv; dz = -dz; }
+                flip ^= 1u << axis;
+            } else {
+                if (axis == 0) px = -dirv;
+                if (axis == 1) py = -dirv;
+                if (axis == 2) pz = -dirv;
+            }
             if (STATS) {
                 ++n_cross;
                 if (code >> 4) ++n_wrap[(code >> 4) - 8];
             }
         }
         const long long pn = ml.idx[m];
+        if (flip) {      // the momentum half was stored by the main path: reverse the reflected components in place
+            PRec<R>* rec = OUTOFPLACE ? a.dst.rec : a.p.rec;
+            PHalf<R> mo = rec[pn].mom;
+            if (flip & 1u) mo.x = -mo.x;
+            if (flip & 2u) mo.y = -mo.y;
+            if (flip & 4u) mo.z = -mo.z;
+            rec[pn].mom = mo;
+        }
         leaves = a.leave_list && (c < a.leave_lo || c >= a.leave_hi);
         leaver = (unsigned)pn;
         if constexpr (OUTOFPLACE) {

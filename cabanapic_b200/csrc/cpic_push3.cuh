@@ -181,6 +181,7 @@ __device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, WarpMove
         float dx = ml.rx[m], dy = ml.ry[m], dz = ml.rz[m];
         const float qq = ml.q[m];
         int c = ml.cell[m];
+        unsigned flip = 0;
         for (;;) {
             float sx, sy, sz, mx, my, mz, v5, dirv;
             const int axis = mover_streak(px, py, pz, dx, dy, dz, qq, sx, sy, sz, mx, my, mz, v5, dirv);
@@ -189,9 +190,16 @@ __device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, WarpMove
             row_add_vec(a.acc + (long long)c * 12, jc);
             if (axis == 3) break;
             const int code = cross_face(c, axis, dirv, a);
-            if (axis == 0) px = -dirv;
-            if (axis == 1) py = -dirv;
-            if (axis == 2) pz = -dirv;
+            if (code & CROSS_REFLECTED) {      // reflecting wall (Boundary::Reflect): stay on the face, turn around
+                if (axis == 0) { px = dirv; dx = -dx; }
+                if (axis == 1) { py = dirv; dy = -dy; }
+                if (axis == 2) { pz = dirv; dz = -dz; }
+                flip ^= 1u << axis;
+            } else {
+                if (axis == 0) px = -dirv;
+                if (axis == 1) py = -dirv;
+                if (axis == 2) pz = -dirv;
+            }
             if (STATS) {
                 ++n_cross;
                 if (code >> 4) ++n_wrap[(code >> 4) - 8];
@@ -203,6 +211,9 @@ __device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, WarpMove
         PRec<float> o;
         o.pos.x = px; o.pos.y = py; o.pos.z = pz; o.pos.w = cell_to_real(c, 0.f);
         o.mom.x = ml.ux[m]; o.mom.y = ml.uy[m]; o.mom.z = ml.uz[m]; o.mom.w = ml.w[m];
+        if (flip & 1u) o.mom.x = -o.mom.x;
+        if (flip & 2u) o.mom.y = -o.mom.y;
+        if (flip & 4u) o.mom.z = -o.mom.z;
         a.dst.rec[pn] = o;
         atomicAdd(a.hist + c, 1u);
     }

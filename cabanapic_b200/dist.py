@@ -731,7 +731,10 @@ class NativeBench:
             self._push_ms += c.last_ms(0) * n          # no per-step sync: the last push of the call stands for all of them
 
     def prepare_timed(self, sort_interval):
-        pass                                            # (the library captures its graph on the first eligible call)
+        """after the warm-up steps: capture the pair-of-steps graph now (nothing executes), so that the timed call only
+        replays it"""
+        if self.use_graph and sort_interval < 0 and self.mode == "slab" and self.world > 1:
+            self.m.prepare_graph(self.k)
 
     def profile(self, on):
         self._profile = bool(on)

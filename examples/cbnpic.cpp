@@ -7,7 +7,7 @@
 // through the facade headers in include/cabanapic/src (every call lands in a hand-written sm_100a
 // kernel through the C ABI).  Differences from the reference driver, all about I/O:
 //   * the per-step ASCII dumps `partloc` / `ex1d` (example.cpp:274-277, a full device->host copy and
-//     an fprintf per particle every step) are opt-in: CPIC_DUMP=1;
+//     an fprintf per particle every step) are opt-in: CPIC_DUMP=1 (CPIC_DUMP_FIELDS=0 keeps partloc only);
 //   * energies.txt is started afresh instead of appended to;
 //   * CPIC_STEPS overrides deck.num_steps, CPIC_SORT_INTERVAL switches the periodic sort on,
 //     CPIC_ENERGY_INTERVAL thins the energy dumps; a wall-clock summary is printed at the end.
@@ -87,7 +87,8 @@ int main(int argc, char* argv[]) {
         const int energy_interval = env_int("CPIC_ENERGY_INTERVAL", 1);
         const bool dump = env_int("CPIC_DUMP", 0) != 0;
         FILE* fptr = dump ? fopen("partloc", "w") : nullptr;
-        FILE* fpfd = dump ? fopen("ex1d", "w") : nullptr;
+        const bool dump_fields = dump && env_int("CPIC_DUMP_FIELDS", 1) != 0;      // (ex1d is nx lines per step)
+        FILE* fpfd = dump_fields ? fopen("ex1d", "w") : nullptr;
         std::remove("energies.txt");
         if (dump) {
             fprintf(fptr, "#step=0\n0 ");
@@ -113,9 +114,11 @@ int main(int argc, char* argv[]) {
             field_solver.advance_b(fields, real_t(0.5) * px, real_t(0.5) * py, real_t(0.5) * pz, nx, ny, nz, ng);
             if (energy_interval > 0 && step % energy_interval == 0)
                 dump_energies(field_solver, fields, step, step * dt, px, py, pz, nx, ny, nz, ng);
-            if (dump) {
+            if (dump_fields) {
                 fprintf(fpfd, "#step=%d\n", step);
                 field_solver.dump_fields(fpfd, fields, 0, 0, 0, dx, dy, dz, nx, ny, nz, ng);
+            }
+            if (dump) {
                 fprintf(fptr, "#step=%d\n%e ", step, step * dt);
                 dump_particles(fptr, particles, 0, 0, 0, dx, dy, dz, nx, ny, nz, ng);
             }
@@ -124,7 +127,8 @@ int main(int argc, char* argv[]) {
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("#%d steps of %ld particles in %.3f s: %.3e particle-steps/s (incl. energy dumps)\n", num_steps,
                (long)num_particles, sec, num_steps * (double)num_particles / sec);
-        if (dump) { fclose(fptr); fclose(fpfd); }
+        if (dump) fclose(fptr);
+        if (dump_fields) fclose(fpfd);
         delete grid;
     }
     deck.finalize();

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "cabanapic_b200.h"
+#include "cabanapic_b200_mgpu.h"
 
 namespace cabanapic {
 
@@ -37,11 +38,29 @@ class Runtime {
         std::exit(1);      // the reference has no error channel either (exit(1), src/fields.h:24,116)
     }
     void destroy() {
-        if (ctx_) cpic_destroy(ctx_);
+        if (mgpu_) cpic_mgpu_destroy(mgpu_);
+        else if (ctx_) cpic_destroy(ctx_);
         ctx_ = nullptr;
+        mgpu_ = nullptr;
     }
     int sort_interval = 0;       // CPIC_SORT_INTERVAL: Cabana::sortByKey cadence (example/example.cpp:224-228)
     long pushes = 0;
+    // Multi-GPU, replicated mode (one process per GPU: CPIC_WORLD, CPIC_RANK, CPIC_MGPU_ID_FILE in the environment): every
+    // process runs the deck's initialisers for the whole box, keeps particles [lo, hi) of the list on its GPU, and
+    // Kokkos::Experimental::contribute -- the call where the reference marks the spot (example/example.cpp:248-254) --
+    // becomes an ncclAllReduce of the accumulator; the field solve is replicated.
+    int world = 1, rank = 0;
+    cpic_mgpu* mgpu() { ctx(); return mgpu_; }
+    // the slice of the particle list this process owns
+    void share(size_t n, size_t& lo, size_t& hi) const { lo = n * (size_t)rank / (size_t)world; hi = n * (size_t)(rank + 1) / (size_t)world; }
+    // Keep the store cell-ordered with the reordering push (cpic_push_reorder) when it pays: large 3-D problems.  Small
+    // decks keep the caller's particle order (it is observable through dump_particles: partloc).  CPIC_KEEP_ORDER=1 /
+    // CPIC_REORDER=1 force either.
+    bool reorder(size_t np) const {
+        if (const char* e = std::getenv("CPIC_KEEP_ORDER")) if (std::atoi(e)) return false;
+        if (const char* e = std::getenv("CPIC_REORDER")) if (std::atoi(e)) return true;
+        return sort_interval == 0 && np >= (size_t)1 << 20 && (size_t)deck.num_cells > 1024;
+    }
     ~Runtime() { destroy(); }
 
     // ---- residency ------------------------------------------------------------------------
@@ -49,9 +68,11 @@ class Runtime {
         Residency& r = p.residency();
         if (r.device_valid) return;
         const auto& h = p.host();
-        check(cpic_upload_particles(ctx(), h.template member_data<0>(), h.template member_data<1>(), h.template member_data<2>(),
-                                    h.template member_data<3>(), h.template member_data<4>(), h.template member_data<5>(),
-                                    h.template member_data<6>(), h.template member_data<7>(), (int64_t)p.size()),
+        size_t lo, hi;
+        share(p.size(), lo, hi);
+        check(cpic_upload_particles(ctx(), h.template member_data<0>() + lo, h.template member_data<1>() + lo, h.template member_data<2>() + lo,
+                                    h.template member_data<3>() + lo, h.template member_data<4>() + lo, h.template member_data<5>() + lo,
+                                    h.template member_data<6>() + lo, h.template member_data<7>() + lo, (int64_t)(hi - lo)),
               "cpic_upload_particles");
         r.device_valid = true;
     }
@@ -86,9 +107,11 @@ class Runtime {
     void refresh_host(const particle_list_t& p) {
         const auto& h = p.host();
         int64_t n = 0;
-        check(cpic_download_particles(ctx(), h.template member_data<0>(), h.template member_data<1>(), h.template member_data<2>(),
-                                      h.template member_data<3>(), h.template member_data<4>(), h.template member_data<5>(),
-                                      h.template member_data<6>(), h.template member_data<7>(), (int64_t)p.size(), &n),
+        size_t lo, hi;
+        share(p.size(), lo, hi);      // (multi-GPU: this process's slice of the mirror; the rest keeps its last host value)
+        check(cpic_download_particles(ctx(), h.template member_data<0>() + lo, h.template member_data<1>() + lo, h.template member_data<2>() + lo,
+                                      h.template member_data<3>() + lo, h.template member_data<4>() + lo, h.template member_data<5>() + lo,
+                                      h.template member_data<6>() + lo, h.template member_data<7>() + lo, (int64_t)(hi - lo), &n),
               "cpic_download_particles");
     }
     void refresh_host(const field_array_t& f) {
@@ -110,6 +133,9 @@ class Runtime {
    private:
     Runtime() {
         if (const char* e = std::getenv("CPIC_SORT_INTERVAL")) sort_interval = std::atoi(e);
+        if (const char* e = std::getenv("CPIC_WORLD")) world = std::atoi(e) > 1 ? std::atoi(e) : 1;
+        if (const char* e = std::getenv("CPIC_RANK")) rank = std::atoi(e);
+        if (rank < 0 || rank >= world) { std::fprintf(stderr, "cabanapic_b200: CPIC_RANK out of range\n"); std::exit(1); }
     }
     void create() {
         cpic_params p{};
@@ -122,11 +148,27 @@ class Runtime {
 #endif
         p.boundary = deck.BOUNDARY_TYPE == Boundary::Periodic ? CPIC_BOUNDARY_PERIODIC : CPIC_BOUNDARY_REFLECT;
         if (const char* e = std::getenv("CPIC_DEVICE")) p.device = std::atoi(e);
+        else if (world > 1) p.device = rank;
         p.fp_mode = CPIC_FP_STRICT;
         if (const char* e = std::getenv("CPIC_FP_CONTRACT")) p.fp_mode = std::atoi(e) ? CPIC_FP_CONTRACT : CPIC_FP_STRICT;
         p.deposit_mode = CPIC_DEPOSIT_AUTO;
         p.max_particles = deck.num_particles > 0 ? deck.num_particles : 0;
         p.enable_sort = 1;
+        if (world > 1) {
+            size_t lo, hi;
+            share((size_t)p.max_particles, lo, hi);
+            p.max_particles = (int64_t)(hi - lo);
+            const char* idf = std::getenv("CPIC_MGPU_ID_FILE");
+            unsigned char id[CPIC_MGPU_ID_BYTES];
+            int rc = cpic_mgpu_bootstrap_file(idf ? idf : "/tmp/cabanapic_b200.nccl_id", rank, world, 120.0, id);
+            if (rc == CPIC_OK) rc = cpic_mgpu_create(&p, rank, world, id, CPIC_MGPU_REPLICATED, 0, &mgpu_);
+            if (rc != CPIC_OK) {
+                std::fprintf(stderr, "cabanapic_b200: multi-GPU start-up failed (%d): %s\n", rc, cpic_mgpu_last_error(nullptr));
+                std::exit(1);
+            }
+            ctx_ = cpic_mgpu_context(mgpu_);
+            return;
+        }
         const int rc = cpic_create(&p, &ctx_);
         if (rc != CPIC_OK) {
             std::fprintf(stderr, "cabanapic_b200: cpic_create failed (%d): %s\n", rc, cpic_last_error(nullptr));
@@ -155,6 +197,7 @@ class Runtime {
     static void scatter_interp(const interpolator_array_t& a, const real_t* in) { scatter_interp_impl(a, in, std::make_index_sequence<18>{}); }
 
     cpic_ctx* ctx_ = nullptr;
+    cpic_mgpu* mgpu_ = nullptr;
 };
 
 template <ArrayKind K, class Members, int VL>
@@ -198,10 +241,17 @@ inline void deep_copy(Dst& dst, const cabanapic::DeviceBacked<K, Members, VL>& s
 namespace Kokkos {
 namespace Experimental {
 inline cabanapic::ScatterHandle create_scatter_view(const cabanapic::Accumulators& a) { return cabanapic::ScatterHandle{a}; }
-// contribute(): where the reference sums thread-private duplicates (example/example.cpp:248).  On one
-// GPU the deposit is already complete; a multi-GPU driver all-reduces here (cabanapic_b200/dist.py).
+// contribute(): where the reference sums thread-private duplicates (example/example.cpp:248).  On one GPU the deposit
+// is already complete; with CPIC_WORLD > 1 processes (replicated mode) it is the ncclAllReduce of the accumulator.
 inline void contribute(const cabanapic::Accumulators&, const cabanapic::ScatterHandle&) {
     cabanapic::Runtime& rt = cabanapic::Runtime::get();
+    if (rt.mgpu()) {
+        if (cpic_mgpu_reduce_accumulator(rt.mgpu()) != CPIC_OK) {
+            std::fprintf(stderr, "cabanapic_b200: cpic_mgpu_reduce_accumulator failed: %s\n", cpic_mgpu_last_error(rt.mgpu()));
+            std::exit(1);
+        }
+        return;
+    }
     rt.check(cpic_contribute(rt.ctx()), "cpic_contribute");
 }
 }  // namespace Experimental

@@ -44,11 +44,17 @@ enum {
     CPIC_E_NOMEM = -3,       /* device allocation failed                     */
     CPIC_E_CAPACITY = -4,    /* more particles than max_particles            */
     CPIC_E_BAD_CELL = -5,    /* particle cell index outside the grid         */
-    CPIC_E_UNSUPPORTED = -6  /* e.g. Boundary::Reflect (reference: exit(1))  */
+    CPIC_E_UNSUPPORTED = -6  /* a combination that is not implemented        */
 };
 
 enum { CPIC_SOLVER_EM = 0, CPIC_SOLVER_ES_1D = 1 };   /* -DSOLVER_TYPE, example/example.cpp:24-35 */
-enum { CPIC_BOUNDARY_REFLECT = 0, CPIC_BOUNDARY_PERIODIC = 1 }; /* enum Boundary, src/input/deck.h:9-12 */
+/* enum Boundary, src/input/deck.h:9-12.  PERIODIC is what the reference runs.  REFLECT is declared there but exits in the
+ * field code (src/fields.h:21-25,113-117) and survives in the mover only as VPIC's commented block (src/move_p.h:298-324);
+ * here it is built: a particle whose streak ends on a domain face keeps its cell, stays on the face and has
+ * its momentum component and remaining displacement along that axis reversed; the field side is a perfectly conducting box
+ * (E_tang = 0 on the six walls, "anti_symmetric_fields" of src/grid.h:4-17; no ghost fold / copy).  EM solver, single
+ * context or replicated multi-GPU mode.  No reference output exists for it: parity is pinned by oracle/cpic_oracle.c only. */
+enum { CPIC_BOUNDARY_REFLECT = 0, CPIC_BOUNDARY_PERIODIC = 1 };
 
 /* Floating-point policy of the particle kernels.
  * STRICT: every multiply/add rounds separately, IEEE sqrt/div -- bit-identical
@@ -104,6 +110,19 @@ const char* cpic_last_error(const cpic_ctx* ctx);   /* ctx may be NULL: error of
  * initialize_interpolator, src/interpolator.cpp:125-172. */
 int  cpic_create(const cpic_params* params, cpic_ctx** out);
 void cpic_destroy(cpic_ctx* ctx);
+/* Multiple species: the reference is single-species through the scalars qsp / me of the deck
+ * (src/input/deck.h:254-261); the VPIC decks it ships show the intended form, one particle list per species pushed
+ * with its own charge and mass into the same accumulator (decks/vpic/2stream-em0.cxx:207-208).  cpic_create_species
+ * gives `parent` (a context of cpic_create) another particle store with its own capacity, sort state and push
+ * constants; it SHARES the parent's field, interpolator and accumulator arrays and its stream, so every entry point of
+ * this header works on it -- uploads / downloads of ITS particles, cpic_push / cpic_push_reorder with ITS cpic_consts
+ * (qsp, qdt_2mc = qsp dt / (2 m c)) deposit into the common J -- while the field-side calls belong to the parent.
+ * Destroy the species before the parent.  cpic_step_species: nsteps of example/example.cpp:221-266 with the push
+ * repeated for every listed species (the parent itself may be one of them) between clear and unload; consts[s] belongs
+ * to species[s], the field constants are taken from consts[0]. */
+int  cpic_create_species(cpic_ctx* parent, int64_t max_particles, cpic_ctx** out);
+int  cpic_step_species(cpic_ctx* ctx, cpic_ctx* const* species, const cpic_consts* consts, int32_t nspecies, int64_t nsteps,
+                       int32_t sort_interval, double* energies);
 int  cpic_sync(cpic_ctx* ctx);
 int  cpic_num_cells(const cpic_ctx* ctx, int64_t* out);
 int  cpic_num_particles(const cpic_ctx* ctx, int64_t* out);

@@ -75,6 +75,11 @@ int  cpic_mgpu_reduce_accumulator(cpic_mgpu* m);
  * (falls back to eager launches if the capture fails).  No host synchronisation. */
 int  cpic_mgpu_step(cpic_mgpu* m, const cpic_consts* k, int64_t nsteps, int32_t sort_interval, int32_t use_graph);
 
+/* Capture the CUDA graph of a pair of steps now, without executing anything (SLAB, after at least two eager steps have
+ * brought every lazily allocated buffer and the device-side particle count into being); cpic_mgpu_step(use_graph)
+ * otherwise captures on its first eligible call.  Returns CPIC_E_UNSUPPORTED when the graph path does not apply. */
+int  cpic_mgpu_prepare_graph(cpic_mgpu* m, const cpic_consts* k);
+
 /* Particles this rank sent to its lower / upper neighbour since creation (SLAB; synchronises). */
 int  cpic_mgpu_migration_counts(cpic_mgpu* m, int64_t out[2]);
 /* ... and in the last step only. */

@@ -152,6 +152,27 @@ class Restatement:
         self.lib.orc_advance_e_stencil(_ptr_array(list(s.f)), C.c_double(px), C.c_double(py), C.c_double(pz),
                                        *self._grid(s), C.c_double(dt_eps0))
 
+    def pec_walls(self, s):
+        """zero the tangential E on the six walls (Boundary::Reflect field side; unpinned by the reference)"""
+        self.lib.orc_pec_walls(_ptr_array(list(s.f)), *self._grid(s))
+
+    def step_reflect(self, s, k: Consts, nsteps=1):
+        """the reference's loop (example/example.cpp:221-266) with reflecting particle walls and PEC field walls"""
+        R = np.float32 if self.prec == "f32" else np.float64
+        h = (float(R(0.5) * R(k.px)), float(R(0.5) * R(k.py)), float(R(0.5) * R(k.pz)))
+        out = []
+        for _ in range(nsteps):
+            self.load_interpolator(s)
+            self.clear_accumulator(s)
+            self.push(s, k, periodic=7 << 4)
+            self.unload_accumulator(s, k)
+            self.advance_b_stencil(s, *h)
+            self.advance_e_stencil(s, k.px, k.py, k.pz, k.dt_eps0)
+            self.pec_walls(s)
+            self.advance_b_stencil(s, *h)
+            out.append(self.energies(s))
+        return np.array(out)
+
     def energies(self, s, solver=0):
         e, b = C.c_double(), C.c_double()
         self.lib.orc_energies(_ptr_array(list(s.f)), C.c_int(solver), *self._grid(s), C.byref(e), C.byref(b))

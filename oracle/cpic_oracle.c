@@ -133,8 +133,13 @@ static inline int leaving_domain(long nx, long ny, long nz, long ix, long iy, lo
  * In move_p the bare literals 3.4e38, 0.5, 2 and (1./3.) are doubles/ints mixed
  * into real arithmetic; the expressions below keep those promotions.
  * Returns the number of faces crossed (the reference returns 0; diagnostics). */
+/* `periodic`: bits 0-2 = per-axis periodic wrap (7 = the reference at HEAD); bits 4-6 = per-axis REFLECTING walls:
+ * Boundary::Reflect, which the reference declares (src/input/deck.h:9-12) but only carries as a commented block
+ * (src/move_p.h:298-324, VPIC's move_p): a particle whose streak ends on a domain face keeps its cell, stays exactly
+ * on the face, and has the momentum component and the remaining displacement along that axis reversed.  No
+ * reference output exists for it: parity for Reflect is UNPINNED by the reference. */
 static int move_particle(real* px, real* py, real* pz, int* pcell, real* acc, real q, real dispx, real dispy,
-                         real dispz, long nx, long ny, long nz, long ng, int periodic) {
+                         real dispz, long nx, long ny, long nz, long ng, int periodic, real* pux, real* puy, real* puz) {
     int crossings = 0;
     for (;;) {
         real mx = *px, my = *py, mz = *pz;
@@ -181,11 +186,22 @@ static int move_particle(real* px, real* py, real* pz, int* pcell, real* acc, re
                 if (face == 4) iy++;
                 if (face == 5) iz++;
                 {
+                    const int refl = periodic >> 4;
+                    const long coord = axis == 0 ? ix : (axis == 1 ? iy : iz), top = axis == 0 ? nx : (axis == 1 ? ny : nz);
+                    if ((refl & (1 << axis)) && (coord == 0 || coord == top + 1)) {
+                        if (axis == 0) { dispx = -dispx; if (pux) *pux = -*pux; }
+                        if (axis == 1) { dispy = -dispy; if (puy) *puy = -*puy; }
+                        if (axis == 2) { dispz = -dispz; if (puz) *puz = -*puz; }
+                        ++crossings;
+                        continue;                       /* same cell, position snapped on the face */
+                    }
+                }
+                {
                     /* periodic = per-axis bit mask (7 = the reference).  An axis whose bit is clear
                      * (slab mode: that ghost layer belongs to a neighbour) neither wraps nor hides
                      * the wrap of another axis, so its tests are skipped. */
                     int lv = leaving_domain(nx, ny, nz, ix, iy, iz);
-                    if (periodic != 7) {
+                    if ((periodic & 7) != 7) {
                         lv = -1;
                         if ((periodic & 1) && ix == 0) lv = 0;
                         if ((periodic & 2) && iy == 0) lv = 1;
@@ -263,7 +279,7 @@ long orc_push(real* dx, real* dy, real* dz, real* ux, real* uy, real* uz, const 
         } else {
             ++movers;
             crossings += move_particle(dx + n, dy + n, dz + n, cell + n, acc, q, vx, vy, vz, nx, ny, nz, ng,
-                                       periodic);
+                                       periodic, ux + n, uy + n, uz + n);
         }
     }
     if (ncross) *ncross = crossings;
@@ -497,6 +513,25 @@ void orc_advance_e_stencil(real* const* f, double px_, double py_, double pz_, l
                 ex[f0] = ex[f0] + (-cj * jfx[f0]) + (py * (cbz[f0] - cbz[fy]) - pz * (cby[f0] - cby[fz]));
                 ey[f0] = ey[f0] + (-cj * jfy[f0]) + (pz * (cbx[f0] - cbx[fz]) - px * (cbz[f0] - cbz[fx]));
                 ez[f0] = ez[f0] + (-cj * jfz[f0]) + (px * (cby[f0] - cby[fx]) - py * (cbx[f0] - cbx[fy]));
+            }
+}
+
+/* Field side of Boundary::Reflect (unpinned by the reference, which exit(1)s in src/fields.h:21-25,113-117): the box is
+ * a perfect conductor -- "anti_symmetric_fields: E_tang = 0" of src/grid.h:4-17, the wall VPIC pairs with reflecting
+ * particles.  The walls are the node planes 1 and n+1 of each axis; the E components tangential to a wall are zeroed
+ * after every E update.  Nothing else is needed: no ghost copy or fold (no particle ever deposits into a ghost cell),
+ * every E value the B update or the interpolator reads at index n+1 is tangential to that wall, and the normal cB on
+ * a wall is never updated (dB_n/dt = -(curl E)_n = 0 there). */
+void orc_pec_walls(real* const* f, long nx, long ny, long nz, long ng) {
+    real *ex = f[F_EX], *ey = f[F_EY], *ez = f[F_EZ];
+    for (long z = 0; z < nz + 2; ++z)
+        for (long y = 0; y < ny + 2; ++y)
+            for (long x = 0; x < nx + 2; ++x) {
+                const long i = vox(x, y, z, nx, ny, ng);
+                const int wx = x == 1 || x == nx + 1, wy = y == 1 || y == ny + 1, wz = z == 1 || z == nz + 1;
+                if (wy || wz) ex[i] = 0;
+                if (wz || wx) ey[i] = 0;
+                if (wx || wy) ez[i] = 0;
             }
 }
 

@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
 def test_argument_validation_without_gpu():
     """Validation happens before any CUDA call, so it is testable here."""
     import cabanapic_b200 as m
-    for kw, code in ((dict(ng=2), -1), (dict(boundary=m.BOUNDARY_REFLECT), -6),
+    for kw, code in ((dict(ng=2), -1), (dict(boundary=m.BOUNDARY_REFLECT, solver=m.SOLVER_ES_1D), -6), (dict(boundary=7), -1),
                      (dict(solver=m.SOLVER_ES_1D, ny=4), -1), (dict(real="f2"), None)):
         args = dict(nx=4, ny=1, nz=1, ng=1)
         args.update({k: v for k, v in kw.items() if k != "real"})

@@ -337,8 +337,8 @@ def test_empty_and_ragged_inputs():
 def test_error_behaviour():
     m = cp()
     with pytest.raises(m.CpicError) as e:
-        m.Context(4, 4, 4, 1, boundary=m.BOUNDARY_REFLECT)
-    assert e.value.code == -6                                 # reference: exit(1) on Reflect
+        m.Context(4, 1, 1, 1, boundary=m.BOUNDARY_REFLECT, solver=m.SOLVER_ES_1D)
+    assert e.value.code == -6                                 # Reflect is built for the EM solver only
     with pytest.raises(m.CpicError):
         m.Context(4, 4, 4, 2)                                 # ng != 1
     with pytest.raises(m.CpicError):
@@ -963,3 +963,99 @@ def test_push_reorder_edge_cases_and_fallbacks():
         a, b = canonical_order(p), canonical_order(s.p)
         for n in PARTICLE_NAMES:
             assert np.array_equal(p[n][a], s.p[n][b]), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid", [(6, 5, 4), (14, 12, 10)])      # few cells (k_push2, block-private) / k_push3
+@pytest.mark.parametrize("fused", [False, True])
+def test_two_species_share_the_accumulator(grid, fused):
+    """two particle lists with their own charge and mass (decks/vpic/2stream-em0.cxx:207-208) pushed
+    into ONE accumulator.  cpic_create_species + cpic_step_species against the oracle running its push twice per step
+    on two particle sets that share the field / interpolator / accumulator arrays: per-species particle state
+    bit-exact in strict mode while the fields agree to summation order (teacher-forced each step)."""
+    from oracle.api import Consts as OConsts
+    nx, ny, nz = grid
+    se = random_state(nx, ny, nz, nppc=20, prec="f32", seed=31)
+    si = random_state(nx, ny, nz, nppc=9, prec="f32", seed=32, uth=0.05)
+    si.f, si.interp, si.acc = se.f, se.interp, se.acc                  # the ions see and feed the same arrays
+    ke = consts_for(nx, ny, nz, "f32", qdt_2mc=-0.05)
+    d = ke.to_dict()
+    d.update(qsp=1.0, qdt_2mc=0.05 / 4.0)                              # ions: opposite charge, four times the mass
+    ki = OConsts(**d)
+    O = Restatement("f32")
+    m = cp()
+    hp = (0.5 * ke.px, 0.5 * ke.py, 0.5 * ke.pz)
+    with make_ctx(se) as c:
+        sp = c.create_species(si.np)
+        try:
+            sp.upload_particles(si.p)
+            for step in range(3):
+                O.load_interpolator(se); O.clear_accumulator(se)
+                O.push(se, ke); O.push(si, ki)
+                O.unload_accumulator(se, ke)
+                O.advance_b(se, *hp); O.advance_e(se, ke.px, ke.py, ke.pz, ke.dt_eps0); O.advance_b(se, *hp)
+                c.step_species([c, sp], [to_k(ke), to_k(ki)], 1, m.SORT_FUSED if fused else 0)
+                for ctx_, s_ in ((c, se), (sp, si)):
+                    p = ctx_.download_particles()
+                    assert len(p["cell"]) == s_.np
+                    a, b = canonical_order(p), canonical_order(s_.p)
+                    for n in PARTICLE_NAMES:
+                        assert np.array_equal(p[n][a], s_.p[n][b]), (step, n)
+                f = c.download_fields()
+                scale = np.abs(se.f).max(axis=1, keepdims=True) + 1e-30
+                assert (np.abs(f - se.f) / scale).max() < 2e-4
+                c.upload_fields(se.f)                                   # teacher-forced: same inputs for the next step
+        finally:
+            sp.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("grid,fused", [((6, 5, 4), False), ((6, 5, 4), True), ((14, 12, 10), True)])
+def test_reflect_boundary_matches_oracle(grid, fused, prec):
+    """SURVEY 8f.3 -- Boundary::Reflect: reflecting particle walls (VPIC's block the reference keeps in comments,
+    src/move_p.h:298-324) + a perfectly conducting box (E_tang = 0, src/grid.h:4-17).  The reference exit(1)s here, so
+    parity is pinned by the oracle restatement only (oracle/cpic_oracle.c: move_particle / orc_pec_walls).  Teacher-
+    forced steps: particle state bit-exact in strict mode (cells, positions on the wall, reversed momenta), fields to
+    summation order; no particle ever leaves the interior; every drain variant (k_push / k_push2 block-private /
+    k_push3) is exercised through the grids and precisions."""
+    if fused and prec == "f64":
+        pytest.skip("the reordering push is float")
+    nx, ny, nz = grid
+    s = random_state(nx, ny, nz, nppc=16, prec=prec, seed=41)
+    k = consts_for(nx, ny, nz, prec)
+    O = Restatement(prec)
+    O.pec_walls(s)
+    m = cp()
+    R = PREC[prec]
+    hp = (float(R(0.5) * R(k.px)), float(R(0.5) * R(k.py)), float(R(0.5) * R(k.pz)))
+    with make_ctx(s, boundary=m.BOUNDARY_REFLECT) as c:
+        c.enable_push_stats(True)
+        reflected = 0
+        for step in range(4):
+            ux0 = s.p["ux"].copy()
+            O.load_interpolator(s); c.load_interpolator_array()
+            O.clear_accumulator(s); c.clear_accumulator_array()
+            movers, crossings = O.push(s, k, periodic=7 << 4)
+            (c.push_reorder if fused else c.push)(to_k(k))
+            st = c.push_stats()
+            assert st["movers"] == movers and st["crossings"] == crossings
+            p = c.download_particles()
+            a, b = canonical_order(p), canonical_order(s.p)
+            for n in PARTICLE_NAMES:
+                assert np.array_equal(p[n][a], s.p[n][b]), (step, n)
+            assert acc_close(c.download_accumulators(), s.acc, prec)
+            O.unload_accumulator(s, k); c.unload_accumulator_array(to_k(k))
+            O.advance_b_stencil(s, *hp); c.advance_b(*hp)
+            O.advance_e_stencil(s, k.px, k.py, k.pz, k.dt_eps0); O.pec_walls(s); c.advance_e(k.px, k.py, k.pz, k.dt_eps0)
+            O.advance_b_stencil(s, *hp); c.advance_b(*hp)
+            f = c.download_fields()
+            scale = np.abs(s.f).max(axis=1, keepdims=True) + 1e-30
+            assert (np.abs(f - s.f) / scale).max() < (2e-4 if prec == "f32" else 1e-11)
+            c.upload_fields(s.f)
+            ix = s.p["cell"] % (nx + 2); iy = (s.p["cell"] // (nx + 2)) % (ny + 2); iz = s.p["cell"] // ((nx + 2) * (ny + 2))
+            assert ix.min() >= 1 and ix.max() <= nx and iy.min() >= 1 and iy.max() <= ny and iz.min() >= 1 and iz.max() <= nz
+            reflected += int(np.sum(np.abs(s.p["dx"]) == 1.0))
+        assert reflected >= 0
+        d = c.state_digest()
+        assert d["particles"] == s.np and d["cells_not_interior"] == 0 and d["offsets_out_of_range"] == 0

@@ -157,3 +157,42 @@ def test_native_replicated_stepper_matches_oracle(tmp_path):
         assert np.array_equal(g["f"], got[0]["f"])                    # replicas stay bit-identical
     _check_state(world, got, s)
     assert np.allclose(got[0]["en"], want_en, rtol=2e-4)
+
+
+def test_weibel_deck_cpp_driver_on_gpus(tmp_path):
+    """BASELINE configs[3] through the C++ host side: examples/cbnpic_mgpu.cpp (deck interface + cpic_mgpu_*, one
+    process per GPU, file rendezvous) runs the Weibel deck in slab mode on min(device_count, 2) GPUs with particle
+    migration; its energy history must agree with the single-GPU facade driver (cbnpic_weibel_3d) on the same deck,
+    no particle may be lost, and particles must really have migrated."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    build = os.path.join(root, "examples", "build")
+    if not os.path.exists(os.path.join(build, "cbnpic_mgpu_weibel_3d")):
+        pytest.skip("examples/build was not produced in the build container")
+    world = _world()
+    env = dict(os.environ, CPIC_WEIBEL_N="24", CPIC_WEIBEL_PPC="8", CPIC_STEPS="40", CPIC_ENERGY_INTERVAL="10")
+    single = tmp_path / "single"
+    single.mkdir()
+    r = subprocess.run([os.path.join(build, "cbnpic_weibel_3d")], cwd=single, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = np.loadtxt(single / "energies.txt", ndmin=2)
+    multi = tmp_path / "multi"
+    multi.mkdir()
+    procs = []
+    for rank in range(world):
+        e = dict(env, CPIC_WORLD=str(world), CPIC_RANK=str(rank), CPIC_MGPU_ID_FILE=str(multi / "id"), CPIC_MGPU_MODE="slab",
+                 CPIC_MGPU_OPEN_Z="1")
+        procs.append(subprocess.Popen([os.path.join(build, "cbnpic_mgpu_weibel_3d")], cwd=multi, env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (o, err) in zip(procs, outs):
+        assert p.returncode == 0, err[-2000:]
+    got = np.loadtxt(multi / "energies.txt", ndmin=2)
+    assert got.shape == want.shape == (4, 4)
+    assert np.allclose(got[:, 2:], want[:, 2:], rtol=2e-3), (got, want)
+    line = [l for l in outs[0][0].splitlines() if l.startswith("#digest:")][0].split()
+    d = dict(zip(line[1::2], line[2::2]))
+    n = 24 ** 3 * 8
+    assert float(d["particles"]) == n and float(d["not-interior"]) == 0 and float(d["offsets-out"]) == 0
+    assert float(d["migrated"]) > 1000
+    assert "z-slab" in outs[0][0]
