@@ -32,6 +32,9 @@ namespace cpic {
 #ifndef PUSH3_MIN_BLOCKS
 #define PUSH3_MIN_BLOCKS 3
 #endif
+#ifndef PUSH3_KO
+#define PUSH3_KO 0
+#endif
 constexpr int PUSH3_WARPS = PUSH3_NWARPS;
 constexpr int PUSH3_CH_MAX = 264;      // cells per chunk (one x-row of the 256^3 deck incl. ghosts = 258)
 constexpr int PUSH3_MOVER_CAP = 64;
@@ -46,6 +49,19 @@ struct Push3Args {
     // traffic lies between them at 256^3 x 64)
     int ch, cpp, gz, plane, yblock, nchunks, nc;
     unsigned* work;          // dynamic work counter (zeroed by the host before the launch)
+#if PUSH3_KO
+    int ko;                  // developer knock-outs (wrong results, timing only): see tools/r2_ko.sh
+#endif
+};
+
+
+// A warp's list of cell-crossers waiting for the drain (the in-kernel form of VPIC's particle_mover_t list the reference
+// kept in comments, src/push.h:271-291): 48-byte entries {x y z cell | rx ry rz slot | ux uy uz w}, three 128-bit words --
+// an append is 3 STS.128 and a drain read 3 LDS.128 (stride 12 words: conflict-free), where thirteen separate arrays
+// cost 13 shared-memory wavefronts per append with only the few mover lanes active.  The charge q = w * qsp is
+// recomputed by the drain (the same single multiplication).
+struct MoverList3 {
+    float4 e[PUSH3_MOVER_CAP * 3];
 };
 
 struct Push3Smem {
@@ -54,7 +70,7 @@ struct Push3Smem {
     unsigned long long mbar;                     // transaction barrier of the two bulk copies
     int chunk;                                   // the chunk the CTA works on (dynamic scheduling)
     int pad_;
-    WarpMoverListP<float, PUSH3_MOVER_CAP> lists[PUSH3_WARPS];
+    MoverList3 lists[PUSH3_WARPS];
     float rows[PUSH3_WARPS][32 * PUSH2_ROW];
     int rcell[PUSH3_WARPS][32];
     int rcnt[PUSH3_WARPS][32];
@@ -171,23 +187,24 @@ __device__ __forceinline__ void segsum_rows3(const float* rows, const int* rcell
 // Drain list entries [first, first+32): the move_p loop (src/move_p.h:93-371) per lane, then ONE 256-bit store of the
 // mover's whole record at the slot the main path claimed for it.
 template <bool FMA, bool STATS>
-__device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, WarpMoverListP<float, PUSH3_MOVER_CAP>& ml, int first,
-                                              int count, int lane, unsigned long long& n_cross, unsigned long long (&n_wrap)[6]) {
+__device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, const MoverList3& ml, int first, int count, int lane,
+                                              unsigned long long& n_cross, unsigned long long (&n_wrap)[6], int ko = 0) {
     const int m = first + lane;
     bool leaves = false;
     unsigned leaver = 0;
     if (lane < count) {
-        float px = ml.x[m], py = ml.y[m], pz = ml.z[m];
-        float dx = ml.rx[m], dy = ml.ry[m], dz = ml.rz[m];
-        const float qq = ml.q[m];
-        int c = ml.cell[m];
+        const float4 e0 = ml.e[3 * m], e1 = ml.e[3 * m + 1], e2 = ml.e[3 * m + 2];
+        float px = e0.x, py = e0.y, pz = e0.z;
+        float dx = e1.x, dy = e1.y, dz = e1.z;
+        const float qq = __fmul_rn(e2.w, a.qsp);
+        int c = __float_as_int(e0.w);
         unsigned flip = 0;
         for (;;) {
             float sx, sy, sz, mx, my, mz, v5, dirv;
             const int axis = mover_streak(px, py, pz, dx, dy, dz, qq, sx, sy, sz, mx, my, mz, v5, dirv);
             float jc[12];
             streak_currents<FMA>(qq, sx, sy, sz, mx, my, mz, v5, jc);
-            row_add_vec(a.acc + (long long)c * 12, jc);
+            if (!(PUSH3_KO && (ko & 64))) row_add_vec(a.acc + (long long)c * 12, jc);
             if (axis == 3) break;
             const int code = cross_face(c, axis, dirv, a);
             if (code & CROSS_REFLECTED) {      // reflecting wall (Boundary::Reflect): stay on the face, turn around
@@ -205,17 +222,19 @@ __device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, WarpMove
                 if (code >> 4) ++n_wrap[(code >> 4) - 8];
             }
         }
-        const unsigned pn = ml.idx[m];
+        const unsigned pn = __float_as_uint(e1.w);
         leaves = a.leave_list && (c < a.leave_lo || c >= a.leave_hi);
         leaver = pn;
         PRec<float> o;
         o.pos.x = px; o.pos.y = py; o.pos.z = pz; o.pos.w = cell_to_real(c, 0.f);
-        o.mom.x = ml.ux[m]; o.mom.y = ml.uy[m]; o.mom.z = ml.uz[m]; o.mom.w = ml.w[m];
+        o.mom.x = e2.x; o.mom.y = e2.y; o.mom.z = e2.z; o.mom.w = e2.w;
         if (flip & 1u) o.mom.x = -o.mom.x;
         if (flip & 2u) o.mom.y = -o.mom.y;
         if (flip & 4u) o.mom.z = -o.mom.z;
-        a.dst.rec[pn] = o;
-        atomicAdd(a.hist + c, 1u);
+        if (!(PUSH3_KO && (ko & 128))) {
+            a.dst.rec[pn] = o;
+            atomicAdd(a.hist + c, 1u);
+        }
     }
     __syncwarp();
     if (a.leave_list) {      // slab mode: list the particles left in a z ghost plane, one counter atomic per warp
@@ -239,7 +258,12 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    WarpMoverListP<float, PUSH3_MOVER_CAP>& ml = sm.lists[warp];
+    MoverList3& ml = sm.lists[warp];
+#if PUSH3_KO
+    const int ko = q.ko;
+#else
+    constexpr int ko = 0;
+#endif
     float* rows = sm.rows[warp];
     int* rcell = sm.rcell[warp];
     int* rcnt = sm.rcnt[warp];
@@ -322,7 +346,15 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             const int cA = validA ? real_to_cell(rA.pos.w) : c0;
             const int cB = validB ? real_to_cell(rB.pos.w) : cA;
             const unsigned oA = (unsigned)(cA - c0), oB = (unsigned)(cB - c0);
-            const bool inA = oA < (unsigned)chn, inB = oB < (unsigned)chn;
+            bool inA = oA < (unsigned)chn, inB = oB < (unsigned)chn;
+#if PUSH3_KO
+            unsigned oA_ = oA, oB_ = oB;
+            if (ko & 16) { if (!inA) oA_ = 0; if (!inB) oB_ = 0; }
+            const bool ginA = inA || (ko & 16), ginB = inB || (ko & 16);
+#else
+            const unsigned oA_ = oA, oB_ = oB;
+            const bool ginA = inA, ginB = inB;
+#endif
             // native: the particle's index lies inside the segment of its own cell
             bool natA = false, natB = false;
             if (validA && inA) { const unsigned lo = sS[oA]; natA = (iA - lo) < (sS[oA + 1] - lo); }
@@ -346,9 +378,11 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             // destination slots (in the segment of the cell the particle is in now); the atomics' round trip overlaps
             // the gather and the Boris rotation
             unsigned base = 0, fsA = 0, fsB = 0;
-            if (mycnt) base = atomicAdd(a.cursor + cf + lane, mycnt);
-            if (forA) fsA = atomicAdd(a.cursor + cA, 1u);
-            if (forB) fsB = atomicAdd(a.cursor + cB, 1u);
+            if (!(PUSH3_KO && (ko & 32))) {
+                if (mycnt) base = atomicAdd(a.cursor + cf + lane, mycnt);
+                if (forA) fsA = atomicAdd(a.cursor + cA, 1u);
+                if (forB) fsB = atomicAdd(a.cursor + cB, 1u);
+            } else { base = iA; fsA = iA; fsB = iB; }
 
             float2 x = make_float2(rA.pos.x, rB.pos.x), y = make_float2(rA.pos.y, rB.pos.y), z = make_float2(rA.pos.z, rB.pos.z);
             float2 ux = make_float2(rA.mom.x, rB.mom.x), uy = make_float2(rA.mom.y, rB.mom.y), uz = make_float2(rA.mom.z, rB.mom.z);
@@ -373,10 +407,10 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                 CPIC_LDI(fB, inB, sb, gb)
 #undef CPIC_LDI
 #else
-                const float4* pa = inA ? reinterpret_cast<const float4*>(sm.ip + oA * 20u)
-                                       : reinterpret_cast<const float4*>(a.ip + (long long)cA * 20);
-                const float4* pb = inB ? reinterpret_cast<const float4*>(sm.ip + oB * 20u)
-                                       : reinterpret_cast<const float4*>(a.ip + (long long)cB * 20);
+                const float4* pa = ginA ? reinterpret_cast<const float4*>(sm.ip + oA_ * 20u)
+                                        : reinterpret_cast<const float4*>(a.ip + (long long)cA * 20);
+                const float4* pb = ginB ? reinterpret_cast<const float4*>(sm.ip + oB_ * 20u)
+                                        : reinterpret_cast<const float4*>(a.ip + (long long)cB * 20);
                 float fA[20], fB[20];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) *reinterpret_cast<float4*>(&fA[4 * k]) = pa[k];
@@ -450,12 +484,12 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             // a stayer's whole record in one full-sector store (a mover's is written by the drain)
             {
                 PRec<float> o;
-                if (stayA) {
+                if (stayA && !(PUSH3_KO && (ko & 1))) {
                     o.pos.x = nx_.x; o.pos.y = ny_.x; o.pos.z = nz_.x; o.pos.w = cell_to_real(cA, 0.f);
                     o.mom.x = pux.x; o.mom.y = puy.x; o.mom.z = puz.x; o.mom.w = w.x;
                     a.dst.rec[dA] = o;
                 }
-                if (stayB) {
+                if (stayB && !(PUSH3_KO && (ko & 1))) {
                     o.pos.x = nx_.y; o.pos.y = ny_.y; o.pos.z = nz_.y; o.pos.w = cell_to_real(cB, 0.f);
                     o.mom.x = pux.y; o.mom.y = puy.y; o.mom.z = puz.y; o.mom.w = w.y;
                     a.dst.rec[dB] = o;
@@ -482,7 +516,7 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                 rcell[lane] = nsA ? cA : (pairB ? cB : -1);
                 rcnt[lane] = (nsA ? 1 : 0) + (pairB ? 1 : 0);
                 // everything else that stays deposits directly: foreigners, and a native B whose pair straddles two cells
-                const bool dirA = stayA && !nsA, dirB = stayB && !pairB;
+                const bool dirA = stayA && !nsA && !(PUSH3_KO && (ko & 4)), dirB = stayB && !pairB && !(PUSH3_KO && (ko & 4));
                 float* const ga = a.acc + (long long)cA * 12;
                 float* const gb = a.acc + (long long)cB * 12;
                 red_add_v4_if(dirA, ga + 0, cur[0].x, cur[1].x, cur[2].x, cur[3].x);
@@ -494,46 +528,46 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                 red_add_v4_if(dirB, gb + 8, cur[8].y, cur[9].y, cur[10].y, cur[11].y);
                 red_add_u32_if(dirB, a.hist + cB, 1u);
                 __syncwarp();
-                segsum_rows3(rows, rcell, rcnt, a.acc, a.hist, lane);
+                if (!(PUSH3_KO && (ko & 8))) segsum_rows3(rows, rcell, rcnt, a.acc, a.hist, lane);
             }
 
             // ---- movers: append to the warp's list, drain densely (src/push.h:261-269 -> move_p)
-            const unsigned mA = __ballot_sync(full, movA), mB = __ballot_sync(full, movB);
+            const unsigned mA = (PUSH3_KO && (ko & 2)) ? 0u : __ballot_sync(full, movA), mB = (PUSH3_KO && (ko & 2)) ? 0u : __ballot_sync(full, movB);
             if (mA | mB) {
                 if (STATS) n_mov += (movA ? 1 : 0) + (movB ? 1 : 0);
                 if (mA) {
                     if (movA) {
                         const int m = nlist + __popc(mA & lt);
-                        ml.x[m] = x.x; ml.y[m] = y.x; ml.z[m] = z.x; ml.rx[m] = ux.x; ml.ry[m] = uy.x; ml.rz[m] = uz.x;
-                        ml.q[m] = qq.x; ml.cell[m] = cA; ml.idx[m] = dA;
-                        ml.ux[m] = pux.x; ml.uy[m] = puy.x; ml.uz[m] = puz.x; ml.w[m] = w.x;
+                        ml.e[3 * m] = make_float4(x.x, y.x, z.x, __int_as_float(cA));
+                        ml.e[3 * m + 1] = make_float4(ux.x, uy.x, uz.x, __uint_as_float(dA));
+                        ml.e[3 * m + 2] = make_float4(pux.x, puy.x, puz.x, w.x);
                     }
                     nlist += __popc(mA);
                     __syncwarp();
                     if (nlist >= 32) {
                         nlist -= 32;
-                        drain_movers3<FMA, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap);
+                        drain_movers3<FMA, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap, ko);
                     }
                 }
                 if (mB) {
                     if (movB) {
                         const int m = nlist + __popc(mB & lt);
-                        ml.x[m] = x.y; ml.y[m] = y.y; ml.z[m] = z.y; ml.rx[m] = ux.y; ml.ry[m] = uy.y; ml.rz[m] = uz.y;
-                        ml.q[m] = qq.y; ml.cell[m] = cB; ml.idx[m] = dB;
-                        ml.ux[m] = pux.y; ml.uy[m] = puy.y; ml.uz[m] = puz.y; ml.w[m] = w.y;
+                        ml.e[3 * m] = make_float4(x.y, y.y, z.y, __int_as_float(cB));
+                        ml.e[3 * m + 1] = make_float4(ux.y, uy.y, uz.y, __uint_as_float(dB));
+                        ml.e[3 * m + 2] = make_float4(pux.y, puy.y, puz.y, w.y);
                     }
                     nlist += __popc(mB);
                     __syncwarp();
                     if (nlist >= 32) {
                         nlist -= 32;
-                        drain_movers3<FMA, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap);
+                        drain_movers3<FMA, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap, ko);
                     }
                 }
             }
             rA = rA_n; rB = rB_n;
         }
     }
-    if (nlist > 0) drain_movers3<FMA, STATS>(a, ml, 0, nlist, lane, n_cross, n_wrap);
+    if (nlist > 0) drain_movers3<FMA, STATS>(a, ml, 0, nlist, lane, n_cross, n_wrap, ko);
 
     if (STATS) {
         __syncwarp();

@@ -35,6 +35,8 @@ def main():
         print(f"in-place push, freshly sorted: {c.last_ms(0):8.3f} ms  {56 * n / c.last_ms(0) / 1e6:8.1f} GB/s", flush=True)
     if mode in ("both", "reorder"):
         for s in range(steps):
+            if s == steps - 1 and os.environ.get("CPIC_KO_LAST"):      # developer knock-outs (a -DPUSH3_KO=1 build), last step only
+                os.environ["CPIC_KO"] = os.environ["CPIC_KO_LAST"]
             c.step(k, 1, cp.SORT_FUSED, False); c.sync()
             print(f"reordering push, step {s}: {c.last_ms(0):8.3f} ms  {56 * n / c.last_ms(0) / 1e6:8.1f} GB/s", flush=True)
 
