@@ -151,6 +151,7 @@ def lib() -> C.CDLL:
             "cpic_mgpu_state_digest": [vp, C.POINTER(dbl)],
             "cpic_mgpu_sync": [vp],
             "cpic_mgpu_used_graph": [vp],
+            "cpic_mgpu_transport": [vp],
         }
         L.cpic_mgpu_last_error.restype = C.c_char_p
         L.cpic_mgpu_last_error.argtypes = [C.c_void_p]
@@ -180,7 +181,8 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
 EXPORTED_MGPU = ["cpic_mgpu_last_error", "cpic_mgpu_unique_id", "cpic_mgpu_bootstrap_file", "cpic_mgpu_create",
                  "cpic_mgpu_destroy", "cpic_mgpu_context", "cpic_mgpu_layout", "cpic_mgpu_init_uniform_plasma",
                  "cpic_mgpu_reduce_accumulator", "cpic_mgpu_step", "cpic_mgpu_prepare_graph", "cpic_mgpu_migration_counts", "cpic_mgpu_last_migration",
-                 "cpic_mgpu_energies", "cpic_mgpu_state_digest", "cpic_mgpu_sync", "cpic_mgpu_used_graph"]
+                 "cpic_mgpu_energies", "cpic_mgpu_state_digest", "cpic_mgpu_sync", "cpic_mgpu_used_graph", "cpic_mgpu_transport"]
+TRANSPORT_NAMES = {0: "none", 1: "nccl", 2: "peer-memory"}
 MGPU_REPLICATED, MGPU_SLAB, MGPU_AUTO = 0, 1, 2
 DIGEST_NAMES = ["particles", "weight_sum", "cells_not_interior", "offsets_out_of_range", "kinetic_energy",
                 "e_energy", "b_energy", "migrated"]
@@ -557,6 +559,11 @@ class Mgpu:
     @property
     def used_graph(self):
         return bool(self.L.cpic_mgpu_used_graph(self.h))
+
+    @property
+    def transport(self):
+        """how the slab exchanges travel: 'peer-memory' (NVLink stores into the neighbours' memory), 'nccl' or 'none'"""
+        return TRANSPORT_NAMES[self.L.cpic_mgpu_transport(self.h)]
 
     def close(self):
         if getattr(self, "h", None):

@@ -107,6 +107,7 @@ struct CtxBase {
     virtual bool few_cells() const = 0;   // grid small enough for the block-private accumulator (k_push2<PRIV>)
     virtual bool is_species_of(const CtxBase* p) const = 0;
     virtual int sync_np() = 0;      // device-count mode -> host-count mode (synchronises); no-op otherwise
+    virtual long long* device_counts() = 0;      // dc (may be null before the first device-counted migration)
     long long fb_steps = 0;         // steps taken in the few-cells fallback of CPIC_SORT_FUSED (sort when % 8 == 0)
     bool dev_count = false;         // slab mode: np lives in dc[0] on the device, the host's np is stale
     virtual int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
@@ -449,6 +450,7 @@ struct Ctx final : CtxBase {
     }
     // ------------------------------------------------------------------ slab migration, counts on the device
     long long* dc = nullptr;            // [0] np [1] error flags [2] [3] leavers of the last extraction
+    long long* device_counts() override { return dc; }
     int enter_dev_count() {
         if (dev_count) return CPIC_OK;
         int rc;
@@ -469,6 +471,7 @@ struct Ctx final : CtxBase {
         np = h[0];
         if (h[1] & 1) return fail(CPIC_E_CAPACITY, "slab_extract_async: leavers exceeded the send-buffer capacity");
         if (h[1] & 4) return fail(CPIC_E_CAPACITY, "slab_append_async: arrivals exceeded the store capacity %lld", cap);
+        if (h[1] & 8) return fail(CPIC_E_CUDA, "multi-GPU exchange: a neighbour rank did not arrive in time");
         if (h[1]) return fail(CPIC_E_CUDA, "slab_extract_async: the leaver list of a push overflowed or was inconsistent");
         return CPIC_OK;
     }

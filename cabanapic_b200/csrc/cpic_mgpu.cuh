@@ -6,6 +6,17 @@
 //   * add planes (ghost accumulator planes, the z sweeps of the J fold) are received into scratch and added by
 //     k_plane_add / k_rect_add;
 //   * the particle migration uses the device-counted extraction / append of the context (cpic_slab_*_async).
+// Transport of the slab exchanges: PEER MEMORY over NVLink / NVSwitch.  At create time every rank exports its mailbox
+// (receive buffers + two arrival flags) and its field arrays through CUDA IPC and maps its two z neighbours'; an exchange
+// is then ONE kernel (k_p2p_put) that stores this rank's planes / leaver records straight into the neighbours' memory --
+// copy planes land in the neighbours' ghost planes themselves, the particle payload is cut to the device-side leaver
+// count -- and raises the neighbours' arrival flags with a system-scope release once its last block is done, followed
+// by a one-warp kernel (k_p2p_wait) that acquires this rank's own flags.  No NCCL kernel, no rendezvous, no host
+// involvement; the sequence numbers live in device memory, so the whole step still replays as a CUDA graph.  Why no
+// credits are needed: between two uses of the same landing buffer the sender has always waited for a later message of
+// the same neighbour, which that neighbour only sends after consuming the earlier one (stream order).  NCCL send/recv
+// (five groups per step, ~110 us each: profiles/r03_slab_timeline_2gpu_256x256x64.log) stays as the fallback when IPC
+// mapping is unavailable (CPIC_MGPU_P2P=0 forces it) and carries the one-time handle exchange.
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
@@ -75,6 +86,87 @@ __global__ void __launch_bounds__(256) k_rect_add(R* __restrict__ dst, const R* 
     const int y = y0 + (int)(i / w), x = x0 + (int)(i % w);
     dst[(long long)y * gx + x] += src[(long long)y * gx + x];
 }
+// ---- peer-memory exchange ------------------------------------------------------------------------------------------------
+struct PutSeg {
+    const char* src;
+    char* dst;                 // in a neighbour's memory (IPC mapping)
+    long long bytes;           // multiple of 4
+    const long long* n_ptr;    // if set: copy min(*n_ptr * elem, bytes) bytes (device-side leaver count)
+    long long elem;
+};
+constexpr int P2P_MAXSEG = 24;
+struct PutArgs {
+    PutSeg seg[P2P_MAXSEG];
+    unsigned* done;                    // block counter (local)
+    unsigned long long* sent;          // [2] messages sent so far: [0] downwards, [1] upwards (local)
+    unsigned long long* flag[2];       // [0] the lower neighbour's "from above" flag, [1] the upper neighbour's "from below" flag
+};
+struct WaitArgs {
+    const unsigned long long* flag[2]; // this rank's arrival flags: [0] from below, [1] from above (null: nothing expected)
+    unsigned long long* expect;        // [2] messages consumed so far (local)
+    long long* err;                    // err[1] |= 8: a neighbour did not arrive in time (this layer's own word)
+    long long* dc;                     // the context's device counts (may be null): dc[1] |= 8 stops its kernels too
+    unsigned long long timeout_ns;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// grid (blocks per segment, segments): 128-bit stores over NVLink; the last block to finish publishes the arrival
+__global__ void __launch_bounds__(256) k_p2p_put(const __grid_constant__ PutArgs a) {
+    const PutSeg& s = a.seg[blockIdx.y];
+    long long bytes = s.bytes;
+    if (s.n_ptr) {
+        long long n = *s.n_ptr;
+        if (n < 0) n = 0;
+        bytes = n * s.elem < bytes ? n * s.elem : bytes;
+    }
+    const long long tid = blockIdx.x * 256LL + threadIdx.x, nthr = gridDim.x * 256LL;
+    long long w0 = 0;                  // 4-byte words already copied by the 128-bit loop
+    if ((((unsigned long long)s.src | (unsigned long long)s.dst) & 15ull) == 0) {
+        const long long n16 = bytes >> 4;
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(s.src);
+        uint4* __restrict__ dst = reinterpret_cast<uint4*>(s.dst);
+        for (long long i = tid; i < n16; i += nthr) dst[i] = src[i];
+        w0 = n16 * 4;
+    }
+    {
+        const unsigned* __restrict__ src = reinterpret_cast<const unsigned*>(s.src);
+        unsigned* __restrict__ dst = reinterpret_cast<unsigned*>(s.dst);
+        for (long long i = w0 + tid; i < (bytes >> 2); i += nthr) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(a.done, 1u) == gridDim.x * gridDim.y - 1u) {
+            *a.done = 0u;
+            __threadfence_system();
+            for (int d = 0; d < 2; ++d)
+                if (a.flag[d]) st_release_sys(a.flag[d], ++a.sent[d]);
+        }
+    }
+}
+__global__ void k_p2p_wait(const WaitArgs a) {
+    const int d = threadIdx.x;
+    if (d >= 2 || !a.flag[d]) return;
+    const unsigned long long want = ++a.expect[d];
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(a.flag[d]) < want) {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > a.timeout_ns) {
+            a.err[1] |= 8;
+            if (a.dc) a.dc[1] |= 8;
+            break;
+        }
+    }
+}
+
 __global__ void k_count_accumulate(const long long* __restrict__ sent, long long* __restrict__ total) {
     total[0] += sent[0]; total[1] += sent[1];
 }
@@ -130,8 +222,77 @@ struct Mgpu {
     // "up" message into from_dn[i] and the upper neighbour's "down" message into from_up[i] -- ONE NCCL group.  With two
     // ranks both neighbours are the same peer; the op order (sends: up, down; receives: from below, from above) keeps the
     // pairs matched.  With one rank it is two device copies.
-    struct Xfer { const void* s_up; const void* s_dn; void* r_dn; void* r_up; size_t bytes; };
+    // p_up / p_dn: where s_up / s_dn land in the upper / lower neighbour's memory (peer-memory transport); n_up / n_dn:
+    // device-side element counts of a struct-of-arrays particle payload (8 member arrays of soa_cap elements each)
+    struct Xfer {
+        const void* s_up; const void* s_dn; void* r_dn; void* r_up; size_t bytes;
+        void* p_up = nullptr; void* p_dn = nullptr;
+        const long long* n_up = nullptr; const long long* n_dn = nullptr; long long soa_cap = 0;
+    };
+    // ---- peer-memory transport state
+    bool p2p = false;
+    char* mail = nullptr;                 // this rank's mailbox (exported): flags, scratch planes, counts, payload buffers
+    size_t mail_bytes = 0;
+    struct MailLayout { long long flags, scratch, cnt, recv_dn, recv_up, send_cap, nz, nc_pad, plane, bytes; } lay{}, peer_lay[2]{};
+    char* peer_mail[2] = {nullptr, nullptr};      // [0] lower, [1] upper neighbour
+    char* peer_fields[2] = {nullptr, nullptr};
+    void* p2p_state = nullptr;            // done (u32 @0), sent[2] (@8), expect[2] (@24), error words (long long[2] @40)
+    unsigned long long p2p_timeout_ns = 120ull * 1000000000ull;
+    char* peer_field(int dir, int m, long long z) const {
+        const MailLayout& L = peer_lay[dir];
+        return peer_fields[dir] + ((size_t)m * L.nc_pad + (size_t)z * L.plane) * rb();
+    }
+    char* peer_scratch(int dir, size_t off) const { return peer_mail[dir] + peer_lay[dir].scratch + off; }
+    int ring_p2p(const Xfer* x, int n, const char* what) {
+        PutArgs a{};
+        int ns = 0;
+        bool to_dn = false, to_up = false, from_dn = false, from_up = false;
+        auto add = [&](const void* src, void* dst, size_t bytes, const long long* np_, long long elem) {
+            if (ns < P2P_MAXSEG) a.seg[ns] = PutSeg{(const char*)src, (char*)dst, (long long)bytes, np_, elem};
+            ++ns;
+        };
+        for (int i = 0; i < n; ++i) {
+            const Xfer& t = x[i];
+            if (t.soa_cap > 0) {          // particle payload: the first *n elements of each of the 8 member arrays
+                for (int k = 0; k < 8; ++k) {      // (cell: int32 = 4 bytes = rb() in float; slab mode is float only)
+                    const size_t off = (size_t)k * t.soa_cap * rb();
+                    const long long cu = peer_lay[1].send_cap, cd = peer_lay[0].send_cap;      // the receivers carve by THEIR capacity
+                    if (t.s_up) add((const char*)t.s_up + off, (char*)t.p_up + (size_t)k * cu * rb(), (size_t)std::min(t.soa_cap, cu) * rb(), t.n_up, (long long)rb());
+                    if (t.s_dn) add((const char*)t.s_dn + off, (char*)t.p_dn + (size_t)k * cd * rb(), (size_t)std::min(t.soa_cap, cd) * rb(), t.n_dn, (long long)rb());
+                }
+            } else {
+                if (t.s_up) add(t.s_up, t.p_up, t.bytes, nullptr, 0);
+                if (t.s_dn) add(t.s_dn, t.p_dn, t.bytes, nullptr, 0);
+            }
+            to_up |= t.s_up != nullptr; to_dn |= t.s_dn != nullptr;
+            from_dn |= t.r_dn != nullptr; from_up |= t.r_up != nullptr;
+        }
+        if (ns > P2P_MAXSEG) return fail(CPIC_E_INVALID, "%s: too many segments for one peer-memory exchange", what);
+        for (int i = 0; i < ns; ++i) if (!a.seg[i].dst) return fail(CPIC_E_INVALID, "%s: peer destination missing", what);
+        char* st = (char*)p2p_state;
+        a.done = (unsigned*)st;
+        a.sent = (unsigned long long*)(st + 8);
+        a.flag[0] = to_dn ? (unsigned long long*)(peer_mail[0] + peer_lay[0].flags + 128) : nullptr;   // their "from above"
+        a.flag[1] = to_up ? (unsigned long long*)(peer_mail[1] + peer_lay[1].flags) : nullptr;         // their "from below"
+        if (ns > 0) {
+            k_p2p_put<<<dim3(32, (unsigned)ns), 256, 0, c->stream>>>(a);
+            ++c->launches;
+            int rc = c->check_launch("k_p2p_put");
+            if (rc) return ctx(rc);
+        }
+        WaitArgs w{};
+        w.flag[0] = from_dn ? (const unsigned long long*)(mail + lay.flags) : nullptr;
+        w.flag[1] = from_up ? (const unsigned long long*)(mail + lay.flags + 128) : nullptr;
+        w.expect = (unsigned long long*)(st + 24);
+        w.err = (long long*)(st + 40);
+        w.dc = c->device_counts();
+        w.timeout_ns = p2p_timeout_ns;
+        k_p2p_wait<<<1, 32, 0, c->stream>>>(w);
+        ++c->launches;
+        return ctx(c->check_launch("k_p2p_wait"));
+    }
     int ring(const Xfer* x, int n, const char* what) {
+        if (p2p) return ring_p2p(x, n, what);
         if (world == 1) {
             for (int i = 0; i < n; ++i) {
                 if (x[i].s_up && x[i].r_dn) cudaMemcpyAsync(x[i].r_dn, x[i].s_up, x[i].bytes, cudaMemcpyDeviceToDevice, c->stream);
@@ -167,6 +328,95 @@ struct Mgpu {
         return c->check_launch("k_rect_add");
     }
 
+    // Map the two z neighbours' mailboxes and field arrays (CUDA IPC; the 64-byte handles and the layouts travel once over
+    // NCCL).  On any failure the NCCL transport stays in place -- but every rank must take the same decision, so the
+    // outcome is agreed on with one more ring exchange.
+    struct Blob { cudaIpcMemHandle_t mail, fields; MailLayout lay; long long ok; long long pad[7]; };
+    int setup_p2p() {
+        Blob mine{}, *dev = nullptr;
+        Blob got[2]{};
+        cudaDeviceSynchronize();      // the mailbox's flags are zero before anybody can learn its address
+        void* fp = nullptr; int64_t n_ = 0, stride = 0;
+        c->device_ptr(16, &fp, &n_, &stride);
+        bool ok = cudaIpcGetMemHandle(&mine.mail, mail) == cudaSuccess && cudaIpcGetMemHandle(&mine.fields, fp) == cudaSuccess;
+        cudaGetLastError();
+        mine.lay = lay; mine.ok = ok ? 1 : 0;
+        if (cudaMalloc(&dev, 3 * sizeof(Blob)) != cudaSuccess) return fail(CPIC_E_NOMEM, "cudaMalloc(IPC handles)");
+        auto exchange = [&]() -> int {
+            cudaMemcpyAsync(dev, &mine, sizeof(Blob), cudaMemcpyHostToDevice, c->stream);
+            Xfer x{dev, dev, dev + 1, dev + 2, sizeof(Blob)};
+            int rc = ring(&x, 1, "IPC handle exchange");
+            if (rc) return rc;
+            cudaMemcpyAsync(got, dev + 1, 2 * sizeof(Blob), cudaMemcpyDeviceToHost, c->stream);
+            return c->cuda(cudaStreamSynchronize(c->stream), "IPC handle exchange");
+        };
+        int rc = exchange();
+        if (rc) { cudaFree(dev); return rc; }
+        ok = ok && got[0].ok && got[1].ok;
+        std::string why = ok ? "" : "cudaIpcGetMemHandle failed on a rank";
+        if (ok) {
+            for (int d = 0; d < 2 && ok; ++d) {
+                if (d == 1 && up == down) { peer_mail[1] = peer_mail[0]; peer_fields[1] = peer_fields[0]; peer_lay[1] = peer_lay[0]; break; }
+                void *pm = nullptr, *pf = nullptr;
+                cudaError_t e1 = cudaIpcOpenMemHandle(&pm, got[d].mail, cudaIpcMemLazyEnablePeerAccess);
+                cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&pf, got[d].fields, cudaIpcMemLazyEnablePeerAccess) : e1;
+                if (e1 != cudaSuccess || e2 != cudaSuccess) {
+                    why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+                    cudaGetLastError();
+                    if (pm) cudaIpcCloseMemHandle(pm);
+                    ok = false;
+                    break;
+                }
+                peer_mail[d] = (char*)pm; peer_fields[d] = (char*)pf; peer_lay[d] = got[d].lay;
+            }
+        }
+        if (ok && cudaMalloc(&p2p_state, 64) != cudaSuccess) { ok = false; why = "cudaMalloc"; }
+        if (ok) cudaMemset(p2p_state, 0, 64);
+        // second round: did everybody succeed?
+        mine.ok = ok ? 1 : 0;
+        rc = exchange();
+        cudaFree(dev);
+        if (rc) return rc;
+        if (!(ok && got[0].ok && got[1].ok)) {
+            teardown_p2p();
+            return fail(CPIC_E_UNSUPPORTED, "%s", ok ? "a neighbour could not map peer memory" : why.c_str());
+        }
+        if (const char* e = getenv("CPIC_P2P_TIMEOUT_S")) p2p_timeout_ns = (unsigned long long)(atof(e) * 1e9);
+        p2p = true;
+        return CPIC_OK;
+    }
+    void teardown_p2p() {
+        if (p2p && comm) {      // nobody may still be storing into my mailbox: one NCCL round trip with both neighbours
+            p2p = false;
+            long long* t = nullptr;
+            if (cudaMalloc(&t, 4 * sizeof(long long)) == cudaSuccess) {
+                Xfer x{t, t + 1, t + 2, t + 3, sizeof(long long)};
+                ring(&x, 1, "teardown");
+                cudaStreamSynchronize(c->stream);
+                cudaFree(t);
+            }
+        }
+        p2p = false;
+        for (int d = 0; d < 2; ++d) {
+            if (d == 1 && up == down) break;
+            if (peer_mail[d]) cudaIpcCloseMemHandle(peer_mail[d]);
+            if (peer_fields[d]) cudaIpcCloseMemHandle(peer_fields[d]);
+        }
+        peer_mail[0] = peer_mail[1] = peer_fields[0] = peer_fields[1] = nullptr;
+        if (p2p_state) { cudaFree(p2p_state); p2p_state = nullptr; }
+        cudaGetLastError();
+    }
+    // did a peer-memory wait time out?  (host-synchronising callers only)
+    int check_p2p() {
+        if (!p2p_state) return CPIC_OK;
+        long long h[2] = {0, 0};
+        cudaMemcpyAsync(h, (char*)p2p_state + 40, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+        int rc = c->cuda(cudaStreamSynchronize(c->stream), "check_p2p");
+        if (rc) return ctx(rc);
+        if (h[1] & 8) return fail(CPIC_E_CUDA, "peer-memory exchange: a neighbour rank did not arrive within %.0f s", p2p_timeout_ns * 1e-9);
+        return CPIC_OK;
+    }
+
     // ---- slab pieces (example/example.cpp:248-266 with the z neighbours woven in)
     int exchange_accumulators(bool with_particles) {
         const long long nz = c->g.nz;
@@ -177,12 +427,20 @@ struct Mgpu {
         Xfer x[3];
         int n = 0;
         x[n++] = Xfer{accp(nz + 1), accp(0), a_dn, a_up, ab};
+        if (p2p) { x[0].p_up = peer_scratch(1, 0); x[0].p_dn = peer_scratch(0, ab); }      // their a_dn / a_up
         if (with_particles) {
             const int rebase_hi = (int)(-nz * plane()), rebase_lo = (int)(nzl_down * plane());
             if ((rc = ctx(c->slab_extract_async(send_lo, send_hi, send_cap, cnt, rebase_lo, rebase_hi)))) return rc;
             x[n++] = Xfer{cnt + 1, cnt + 0, cnt + 2, cnt + 3, sizeof(long long)};
             const size_t pb = (size_t)send_cap * (7 * rb() + 4);
             x[n++] = Xfer{send_hi, send_lo, recv_dn, recv_up, pb};
+            if (p2p) {
+                x[1].p_up = peer_mail[1] + peer_lay[1].cnt + 2 * sizeof(long long);      // their cnt[2]: received from below
+                x[1].p_dn = peer_mail[0] + peer_lay[0].cnt + 3 * sizeof(long long);      // their cnt[3]: received from above
+                x[2].p_up = peer_mail[1] + peer_lay[1].recv_dn;
+                x[2].p_dn = peer_mail[0] + peer_lay[0].recv_up;
+                x[2].n_up = cnt + 1; x[2].n_dn = cnt + 0; x[2].soa_cap = send_cap;
+            }
         }
         if ((rc = ring(x, n, "accumulator / particle exchange"))) return rc;
         if ((rc = plane_add_any(accp(1), a_dn, plane() * 12))) return rc;       // the lower neighbour's high ghost plane is my plane 1
@@ -203,7 +461,10 @@ struct Mgpu {
         const long long nz = c->g.nz;
         const size_t pb = (size_t)plane() * rb();
         Xfer x[3];
-        for (int i = 0; i < 3; ++i) x[i] = Xfer{field(m0 + i, nz), field(m0 + i, 1), field(m0 + i, 0), field(m0 + i, nz + 1), pb};
+        for (int i = 0; i < 3; ++i) {
+            x[i] = Xfer{field(m0 + i, nz), field(m0 + i, 1), field(m0 + i, 0), field(m0 + i, nz + 1), pb};
+            if (p2p) { x[i].p_up = peer_field(1, m0 + i, 0); x[i].p_dn = peer_field(0, m0 + i, peer_lay[0].nz + 1); }
+        }
         return ring(x, 3, "ghost-plane copy");
     }
     int slab_advance_b(double hx, double hy, double hz) {
@@ -222,6 +483,7 @@ struct Mgpu {
         char* rx = scratch;
         char* ry = scratch + pb;
         Xfer x[2] = {Xfer{field(F_JFX, nz + 1), nullptr, rx, nullptr, pb}, Xfer{field(F_JFY, nz + 1), nullptr, ry, nullptr, pb}};
+        if (p2p) { x[0].p_up = peer_scratch(1, 0); x[1].p_up = peer_scratch(1, pb); }      // their rx / ry
         if ((rc = ring(x, 2, "J fold planes"))) return rc;
         if ((rc = rect_add(field(F_JFY, 1), ry, 1, ny + 1, 1, nx + 2))) return rc;      // :146-151
         if ((rc = ctx(c->fold_phase(1)))) return rc;
@@ -397,12 +659,35 @@ int cpic_mgpu_create(const cpic_params* global, int32_t rank, int32_t world, con
     if (open_z) {
         const long long per_plane_cap = global->max_particles / std::max(1, m->nzl);
         m->send_cap = send_capacity > 0 ? send_capacity : std::max<long long>(4096, per_plane_cap / 20);
+        m->send_cap = (m->send_cap + 63) & ~63ll;      // member arrays of the payload stay 16-byte aligned
         const size_t pb = (size_t)m->send_cap * (7 * m->rb() + 4);
-        for (char** b : {&m->send_lo, &m->send_hi, &m->recv_dn, &m->recv_up})
+        for (char** b : {&m->send_lo, &m->send_hi})
             if (cudaMalloc(b, pb) != cudaSuccess) return bail(CPIC_E_NOMEM, "cudaMalloc(migration buffers)");
-        if (cudaMalloc(&m->cnt, 6 * sizeof(long long)) != cudaSuccess) return bail(CPIC_E_NOMEM, "cudaMalloc");
-        cudaMemset(m->cnt, 0, 6 * sizeof(long long));
-        if (cudaMalloc(&m->scratch, (size_t)m->plane() * 12 * m->rb() * 2) != cudaSuccess) return bail(CPIC_E_NOMEM, "cudaMalloc(plane scratch)");
+        // everything a neighbour writes into lives in ONE allocation, the mailbox (exported through CUDA IPC below)
+        auto up256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        Mgpu::MailLayout& L = m->lay;
+        size_t off = 0;
+        L.flags = (long long)off; off += 256;
+        L.cnt = (long long)off; off += 256;
+        L.scratch = (long long)off; off = up256(off + (size_t)m->plane() * 12 * m->rb() * 2);
+        L.recv_dn = (long long)off; off = up256(off + pb);
+        L.recv_up = (long long)off; off = up256(off + pb);
+        L.bytes = (long long)off; L.send_cap = m->send_cap; L.nz = c->g.nz; L.plane = m->plane();
+        { void* fp = nullptr; int64_t n_ = 0, stride = 0; c->device_ptr(16, &fp, &n_, &stride); L.nc_pad = stride; }
+        if (cudaMalloc(&m->mail, off) != cudaSuccess) return bail(CPIC_E_NOMEM, "cudaMalloc(mailbox)");
+        m->mail_bytes = off;
+        cudaMemset(m->mail, 0, 512);
+        m->cnt = reinterpret_cast<long long*>(m->mail + L.cnt);
+        m->scratch = m->mail + L.scratch;
+        m->recv_dn = m->mail + L.recv_dn;
+        m->recv_up = m->mail + L.recv_up;
+        if (world > 1) {
+            const char* e = getenv("CPIC_MGPU_P2P");
+            if (!e || atoi(e) != 0) {
+                const int prc = m->setup_p2p();
+                if (prc) fprintf(stderr, "[cabanapic_b200 rank %d] peer-memory exchange unavailable (%s): using NCCL send/recv\n", rank, m->err.c_str());
+            }
+        }
     }
     *out = reinterpret_cast<cpic_mgpu*>(m);
     return CPIC_OK;
@@ -413,11 +698,18 @@ void cpic_mgpu_destroy(cpic_mgpu* mm) {
     Mgpu* m = reinterpret_cast<Mgpu*>(mm);
     if (m->c) { cudaSetDevice(m->c->prm.device); cudaStreamSynchronize(m->c->stream); }
     if (m->gexec) cudaGraphExecDestroy(m->gexec);      // the graph references NCCL work: release it before the communicator
+    m->teardown_p2p();
     if (m->comm) g_nccl.CommDestroy(m->comm);
-    cudaFree(m->send_lo); cudaFree(m->send_hi); cudaFree(m->recv_dn); cudaFree(m->recv_up);
-    cudaFree(m->cnt); cudaFree(m->scratch); cudaFree(m->diag);
+    cudaFree(m->send_lo); cudaFree(m->send_hi); cudaFree(m->mail); cudaFree(m->diag);
     if (m->c) cpic_destroy(reinterpret_cast<cpic_ctx*>(m->c));
     delete m;
+}
+
+int cpic_mgpu_transport(const cpic_mgpu* mm) {
+    if (!mm) return CPIC_MGPU_TRANSPORT_NONE;
+    const Mgpu* m = reinterpret_cast<const Mgpu*>(mm);
+    if (m->world == 1) return CPIC_MGPU_TRANSPORT_NONE;
+    return m->p2p ? CPIC_MGPU_TRANSPORT_PEER_MEMORY : CPIC_MGPU_TRANSPORT_NCCL;
 }
 
 cpic_ctx* cpic_mgpu_context(cpic_mgpu* m) { return m ? reinterpret_cast<cpic_ctx*>(reinterpret_cast<Mgpu*>(m)->c) : nullptr; }
@@ -510,7 +802,7 @@ static int mgpu_counts(Mgpu* m, int off, int64_t out[2]) {
     if (!rc) rc = m->c->cuda(cudaStreamSynchronize(m->c->stream), "migration_counts");
     if (rc) return m->ctx(rc);
     out[0] = h[0]; out[1] = h[1];
-    return CPIC_OK;
+    return m->check_p2p();
 }
 int cpic_mgpu_migration_counts(cpic_mgpu* mm, int64_t out[2]) { MGPU_OR_FAIL(mm); if (!out) return CPIC_E_INVALID; return mgpu_counts(m, 4, out); }
 int cpic_mgpu_last_migration(cpic_mgpu* mm, int64_t out[2]) { MGPU_OR_FAIL(mm); if (!out) return CPIC_E_INVALID; return mgpu_counts(m, 0, out); }

@@ -715,6 +715,7 @@ class NativeBench:
         self.use_graph = not os.environ.get("CPIC_NO_GRAPH")
         self.m = _lib.Mgpu(d.nx, d.ny, d.nz, self.rank, self.world, uid, mode=mode, max_particles=cap, real=d.real,
                            device=self.local, fp_mode=self.fp, send_capacity=send_cap)
+        self.transport = self.m.transport
         self.m.init_uniform_plasma(d.nppc, weight=self.we)
         self.m.sync()
 
@@ -758,8 +759,10 @@ class NativeBench:
     def describe(self):
         how = "two steps per CUDA-graph replay" if self.used_graph else "eager launches"
         if self.mode == "slab":
-            return (f"{self.world} z-slabs, native C++ stepper (cpic_mgpu_step): NCCL ghost-plane exchange + device-counted "
-                    f"particle migration, {how}")
+            via = {"peer-memory": "peer-memory (NVLink stores into the neighbours' mailboxes / ghost planes, CUDA IPC)",
+                   "nccl": "NCCL send/recv"}.get(self.transport, self.transport)
+            return (f"{self.world} z-slabs, native C++ stepper (cpic_mgpu_step): ghost-plane exchange + device-counted "
+                    f"particle migration over {via}, {how}")
         return f"grid replicated on {self.world} GPUs, particles split, ncclAllReduce of the accumulator (cpic_mgpu_step)"
 
     def e2e(self, steps, sort_interval):

@@ -61,6 +61,13 @@ void cpic_mgpu_destroy(cpic_mgpu* m);
 cpic_ctx* cpic_mgpu_context(cpic_mgpu* m);
 int  cpic_mgpu_layout(const cpic_mgpu* m, int32_t* mode, int32_t* z0, int32_t* nzl);
 
+/* How the slab exchanges travel.  PEER_MEMORY (the default when the ranks can map each other's memory through CUDA
+ * IPC): one kernel stores the boundary planes / leaver records straight into the z neighbours' memory over NVLink /
+ * NVSwitch and raises their arrival flags; NCCL: ncclSend / ncclRecv groups (fallback; CPIC_MGPU_P2P=0 forces it);
+ * NONE: a single rank.  CPIC_P2P_TIMEOUT_S (default 120) bounds the wait for a neighbour. */
+enum { CPIC_MGPU_TRANSPORT_NONE = 0, CPIC_MGPU_TRANSPORT_NCCL = 1, CPIC_MGPU_TRANSPORT_PEER_MEMORY = 2 };
+int  cpic_mgpu_transport(const cpic_mgpu* m);
+
 /* This rank's share of the synthetic uniform plasma of cpic_init_uniform_plasma over the GLOBAL box:
  * SLAB: the particles of the planes it owns; REPLICATED: global particles [N*rank/world, N*(rank+1)/world). */
 int  cpic_mgpu_init_uniform_plasma(cpic_mgpu* m, int32_t nppc, uint64_t seed, double vthx, double vthy, double vthz,

@@ -49,6 +49,7 @@ def _worker(rank, world, idfile, outdir, mode, graph):
         m = cp.Mgpu(nx, ny, nz, rank, world, uid.raw, mode=cp.MGPU_REPLICATED, max_particles=hi - lo, device=rank)
     m.ctx.upload_particles(p)
     m.ctx.upload_fields(lf)
+    transport = m.transport
     mig, en = [], []
     if graph:                                          # whole run in two calls: eager warm-up, then graph replay
         m.step(k, 3, cp.SORT_FUSED, use_graph=True)
@@ -66,7 +67,7 @@ def _worker(rank, world, idfile, outdir, mode, graph):
     out["cell"] = out["cell"] + z0 * (nx + 2) * (ny + 2)
     f = m.ctx.download_fields()
     m.close()
-    np.savez(os.path.join(outdir, f"r{rank}.npz"), f=f, mig=np.array(mig), en=np.array(en), z0=z0, nzl=nzl, used=used,
+    np.savez(os.path.join(outdir, f"r{rank}.npz"), f=f, mig=np.array(mig), en=np.array(en), z0=z0, nzl=nzl, used=used, transport=transport,
              digest=np.array([dg[n] for n in _lib.DIGEST_NAMES]), tot=np.array(tot), **{"p_" + n: out[n] for n in PARTICLE_NAMES})
 
 
@@ -75,7 +76,16 @@ def _run(tmp_path, mode, graph):
     world = _world()
     idfile = str(tmp_path / "nccl_id")
     mp.spawn(_worker, args=(world, idfile, str(tmp_path), mode, graph), nprocs=world, join=True)
-    return world, [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    got = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    if mode == "slab" and world > 1:      # peer memory unless CPIC_MGPU_P2P=0 asks for NCCL (or IPC mapping is refused: stderr says so)
+        tr = {str(g["transport"]) for g in got}
+        print("slab transport:", tr)
+        assert len(tr) == 1 and tr <= {"peer-memory", "nccl"}, tr
+        if os.environ.get("CPIC_MGPU_P2P") == "0":
+            assert tr == {"nccl"}
+        if os.environ.get("CPIC_REQUIRE_P2P") == "1":
+            assert tr == {"peer-memory"}
+    return world, got
 
 
 def _oracle(world):
