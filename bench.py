@@ -516,13 +516,16 @@ def side_lines(device):
         out["c2_two_stream_1e8_es"] = {"error": str(ex)[:300]}
     # C1 / C3 through the facade binaries
     from oracle.api import RefLib
-    for key, exe, deck, steps in (("c1_two_stream_em_facade", "cbnpic_2stream-em", "2stream-em", 2000),
-                                  ("c3_dioctron_3d_facade", "cbnpic_dioctron_3d", "dioctron_3d", 2000)):
+    # (C4: the Weibel deck at 128^3 x 32 ppc = 6.7e7 particles through the facade's push<> / advance_* calls, default settings)
+    for key, exe, deck, steps, extra_env in (("c1_two_stream_em_facade", "cbnpic_2stream-em", "2stream-em", 2000, {}),
+                                             ("c3_dioctron_3d_facade", "cbnpic_dioctron_3d", "dioctron_3d", 2000, {}),
+                                             ("c4_weibel_3d_facade", "cbnpic_weibel_3d", None, 24, {"CPIC_WEIBEL_N": "128", "CPIC_WEIBEL_PPC": "32"})):
         path = os.path.join(ROOT, "examples", "build", exe)
         try:
             if not os.path.exists(path):
                 raise RuntimeError(f"{path} not built")
             env = dict(os.environ, CPIC_STEPS=str(steps), CPIC_ENERGY_INTERVAL="0", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)))
+            env.update(extra_env)
             r = subprocess.run([path], capture_output=True, text=True, timeout=300, env=env, cwd="/tmp")
             m = re.search(r"#(\d+) steps of (\d+) particles in ([0-9.]+) s: ([0-9.e+]+) particle-steps/s", r.stdout)
             if not m:
@@ -530,7 +533,7 @@ def side_lines(device):
             e = {"steps": int(m.group(1)), "particles": int(m.group(2)), "seconds": float(m.group(3)),
                  "value": float(m.group(4)), "unit": "particle-steps/s", "steps_per_s": int(m.group(1)) / float(m.group(3)),
                  "path": f"examples/build/{exe} (C++ facade over the C ABI, default settings, wall clock incl. launches)"}
-            if RefLib.available(deck, "f32"):
+            if deck and RefLib.available(deck, "f32"):
                 R = RefLib(deck, "f32").create_from_deck(solver=0)
                 kk, _, _ = R.deck_consts()
                 R.run(kk, 20)

@@ -7,14 +7,18 @@
 //     k_plane_add / k_rect_add;
 //   * the particle migration uses the device-counted extraction / append of the context (cpic_slab_*_async).
 // Transport of the slab exchanges: PEER MEMORY over NVLink / NVSwitch.  At create time every rank exports its mailbox
-// (receive buffers + two arrival flags) and its field arrays through CUDA IPC and maps its two z neighbours'; an exchange
-// is then ONE kernel (k_p2p_put) that stores this rank's planes / leaver records straight into the neighbours' memory --
-// copy planes land in the neighbours' ghost planes themselves, the particle payload is cut to the device-side leaver
-// count -- and raises the neighbours' arrival flags with a system-scope release once its last block is done, followed
+// (receive buffers + two arrival flags) through CUDA IPC and maps its two z neighbours'; an exchange
+// is then ONE kernel (k_p2p_put) that stores this rank's planes / leaver records straight into the neighbours' mailboxes
+// -- the particle payload cut to the device-side leaver count -- and raises the neighbours' arrival flags with a system-scope release once its last block is done, followed
 // by a one-warp kernel (k_p2p_wait) that acquires this rank's own flags.  No NCCL kernel, no rendezvous, no host
 // involvement; the sequence numbers live in device memory, so the whole step still replays as a CUDA graph.  Why no
 // credits are needed: between two uses of the same landing buffer the sender has always waited for a later message of
-// the same neighbour, which that neighbour only sends after consuming the earlier one (stream order).  NCCL send/recv
+// the same neighbour, which that neighbour only sends after consuming the earlier one (stream order) -- every landing
+// buffer is reused two or more phases later (accumulator planes / J fold planes share scratch, the cB and J copy planes
+// have their own slots).  Nothing lands in
+// the field arrays themselves: a neighbour may be a whole phase ahead, and this rank's own x/y ghost passes still write
+// the z ghost planes then (measured: in-place landing changed 13 of 3.4e7 migrations at 8 ranks) -- ghost planes are
+// unpacked from the mailbox by k_planes_unpack after the wait.  NCCL send/recv
 // (five groups per step, ~110 us each: profiles/r03_slab_timeline_2gpu_256x256x64.log) stays as the fallback when IPC
 // mapping is unavailable (CPIC_MGPU_P2P=0 forces it) and carries the one-time handle exchange.
 #pragma once
@@ -150,6 +154,12 @@ __global__ void __launch_bounds__(256) k_p2p_put(const __grid_constant__ PutArgs
         }
     }
 }
+// test hook (CPIC_P2P_SKEW_US): holds a rank back before it sends, so that the tests see neighbours a phase apart
+__global__ void k_p2p_skew(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { __nanosleep(1000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
 __global__ void k_p2p_wait(const WaitArgs a) {
     const int d = threadIdx.x;
     if (d >= 2 || !a.flag[d]) return;
@@ -165,6 +175,18 @@ __global__ void k_p2p_wait(const WaitArgs a) {
             break;
         }
     }
+}
+
+// copy planes out of the mailbox into the z ghost planes: blockIdx.y = (direction, member)
+struct UnpackArgs { const char* src[6]; char* dst[6]; long long bytes; };
+__global__ void __launch_bounds__(256) k_planes_unpack(const UnpackArgs a) {
+    const uint4* __restrict__ s = reinterpret_cast<const uint4*>(a.src[blockIdx.y]);
+    uint4* __restrict__ d = reinterpret_cast<uint4*>(a.dst[blockIdx.y]);
+    const long long n16 = a.bytes >> 4;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n16; i += gridDim.x * 256LL) d[i] = s[i];
+    const unsigned* __restrict__ s4 = reinterpret_cast<const unsigned*>(a.src[blockIdx.y]);
+    unsigned* __restrict__ d4 = reinterpret_cast<unsigned*>(a.dst[blockIdx.y]);
+    for (long long i = n16 * 4 + blockIdx.x * 256LL + threadIdx.x; i < (a.bytes >> 2); i += gridDim.x * 256LL) d4[i] = s4[i];
 }
 
 __global__ void k_count_accumulate(const long long* __restrict__ sent, long long* __restrict__ total) {
@@ -233,14 +255,18 @@ struct Mgpu {
     bool p2p = false;
     char* mail = nullptr;                 // this rank's mailbox (exported): flags, scratch planes, counts, payload buffers
     size_t mail_bytes = 0;
-    struct MailLayout { long long flags, scratch, cnt, recv_dn, recv_up, send_cap, nz, nc_pad, plane, bytes; } lay{}, peer_lay[2]{};
+    struct MailLayout { long long flags, scratch, cnt, recv_dn, recv_up, send_cap, nz, nc_pad, plane, bytes, copy; } lay{}, peer_lay[2]{};
     char* peer_mail[2] = {nullptr, nullptr};      // [0] lower, [1] upper neighbour
-    char* peer_fields[2] = {nullptr, nullptr};
     void* p2p_state = nullptr;            // done (u32 @0), sent[2] (@8), expect[2] (@24), error words (long long[2] @40)
     unsigned long long p2p_timeout_ns = 120ull * 1000000000ull;
-    char* peer_field(int dir, int m, long long z) const {
-        const MailLayout& L = peer_lay[dir];
-        return peer_fields[dir] + ((size_t)m * L.nc_pad + (size_t)z * L.plane) * rb();
+    unsigned long long p2p_skew_ns = 0;   // test hook: ranks with rank % 3 == 1 idle this long before every send
+    // landing area of the copy planes in a mailbox: per kind (0: cB, 1: J) [from below: 3 planes][from above: 3 planes],
+    // plane stride 256-aligned.  J and cB planes must NOT share slots: their exchanges are consecutive phases, and a
+    // neighbour that has my J planes already may send its cB planes before I have unpacked its J planes (a landing
+    // buffer is safe to reuse two phases later: the neighbour's next message to me is sent after its unpack).
+    size_t copy_stride() const { return ((size_t)plane() * rb() + 255) & ~(size_t)255; }
+    char* copy_slot(char* mailbox, const MailLayout& L, int kind, int from, int i) const {
+        return mailbox + L.copy + (size_t)((kind * 2 + from) * 3 + i) * copy_stride();
     }
     char* peer_scratch(int dir, size_t off) const { return peer_mail[dir] + peer_lay[dir].scratch + off; }
     int ring_p2p(const Xfer* x, int n, const char* what) {
@@ -274,6 +300,7 @@ struct Mgpu {
         a.sent = (unsigned long long*)(st + 8);
         a.flag[0] = to_dn ? (unsigned long long*)(peer_mail[0] + peer_lay[0].flags + 128) : nullptr;   // their "from above"
         a.flag[1] = to_up ? (unsigned long long*)(peer_mail[1] + peer_lay[1].flags) : nullptr;         // their "from below"
+        if (p2p_skew_ns && rank % 3 == 1) k_p2p_skew<<<1, 1, 0, c->stream>>>(p2p_skew_ns);
         if (ns > 0) {
             k_p2p_put<<<dim3(32, (unsigned)ns), 256, 0, c->stream>>>(a);
             ++c->launches;
@@ -328,17 +355,15 @@ struct Mgpu {
         return c->check_launch("k_rect_add");
     }
 
-    // Map the two z neighbours' mailboxes and field arrays (CUDA IPC; the 64-byte handles and the layouts travel once over
+    // Map the two z neighbours' mailboxes (CUDA IPC; the 64-byte handles and the layouts travel once over
     // NCCL).  On any failure the NCCL transport stays in place -- but every rank must take the same decision, so the
     // outcome is agreed on with one more ring exchange.
-    struct Blob { cudaIpcMemHandle_t mail, fields; MailLayout lay; long long ok; long long pad[7]; };
+    struct Blob { cudaIpcMemHandle_t mail; MailLayout lay; long long ok; long long pad[5]; };
     int setup_p2p() {
         Blob mine{}, *dev = nullptr;
         Blob got[2]{};
         cudaDeviceSynchronize();      // the mailbox's flags are zero before anybody can learn its address
-        void* fp = nullptr; int64_t n_ = 0, stride = 0;
-        c->device_ptr(16, &fp, &n_, &stride);
-        bool ok = cudaIpcGetMemHandle(&mine.mail, mail) == cudaSuccess && cudaIpcGetMemHandle(&mine.fields, fp) == cudaSuccess;
+        bool ok = cudaIpcGetMemHandle(&mine.mail, mail) == cudaSuccess;
         cudaGetLastError();
         mine.lay = lay; mine.ok = ok ? 1 : 0;
         if (cudaMalloc(&dev, 3 * sizeof(Blob)) != cudaSuccess) return fail(CPIC_E_NOMEM, "cudaMalloc(IPC handles)");
@@ -356,18 +381,16 @@ struct Mgpu {
         std::string why = ok ? "" : "cudaIpcGetMemHandle failed on a rank";
         if (ok) {
             for (int d = 0; d < 2 && ok; ++d) {
-                if (d == 1 && up == down) { peer_mail[1] = peer_mail[0]; peer_fields[1] = peer_fields[0]; peer_lay[1] = peer_lay[0]; break; }
-                void *pm = nullptr, *pf = nullptr;
-                cudaError_t e1 = cudaIpcOpenMemHandle(&pm, got[d].mail, cudaIpcMemLazyEnablePeerAccess);
-                cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&pf, got[d].fields, cudaIpcMemLazyEnablePeerAccess) : e1;
-                if (e1 != cudaSuccess || e2 != cudaSuccess) {
-                    why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+                if (d == 1 && up == down) { peer_mail[1] = peer_mail[0]; peer_lay[1] = peer_lay[0]; break; }
+                void* pm = nullptr;
+                const cudaError_t e1 = cudaIpcOpenMemHandle(&pm, got[d].mail, cudaIpcMemLazyEnablePeerAccess);
+                if (e1 != cudaSuccess) {
+                    why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e1);
                     cudaGetLastError();
-                    if (pm) cudaIpcCloseMemHandle(pm);
                     ok = false;
                     break;
                 }
-                peer_mail[d] = (char*)pm; peer_fields[d] = (char*)pf; peer_lay[d] = got[d].lay;
+                peer_mail[d] = (char*)pm; peer_lay[d] = got[d].lay;
             }
         }
         if (ok && cudaMalloc(&p2p_state, 64) != cudaSuccess) { ok = false; why = "cudaMalloc"; }
@@ -382,6 +405,7 @@ struct Mgpu {
             return fail(CPIC_E_UNSUPPORTED, "%s", ok ? "a neighbour could not map peer memory" : why.c_str());
         }
         if (const char* e = getenv("CPIC_P2P_TIMEOUT_S")) p2p_timeout_ns = (unsigned long long)(atof(e) * 1e9);
+        if (const char* e = getenv("CPIC_P2P_SKEW_US")) p2p_skew_ns = (unsigned long long)(atof(e) * 1e3);
         p2p = true;
         return CPIC_OK;
     }
@@ -400,9 +424,8 @@ struct Mgpu {
         for (int d = 0; d < 2; ++d) {
             if (d == 1 && up == down) break;
             if (peer_mail[d]) cudaIpcCloseMemHandle(peer_mail[d]);
-            if (peer_fields[d]) cudaIpcCloseMemHandle(peer_fields[d]);
         }
-        peer_mail[0] = peer_mail[1] = peer_fields[0] = peer_fields[1] = nullptr;
+        peer_mail[0] = peer_mail[1] = nullptr;
         if (p2p_state) { cudaFree(p2p_state); p2p_state = nullptr; }
         cudaGetLastError();
     }
@@ -460,12 +483,26 @@ struct Mgpu {
     int exchange_copy_planes(int m0) {
         const long long nz = c->g.nz;
         const size_t pb = (size_t)plane() * rb();
+        const int kind = m0 == F_JFX ? 1 : 0;
         Xfer x[3];
         for (int i = 0; i < 3; ++i) {
             x[i] = Xfer{field(m0 + i, nz), field(m0 + i, 1), field(m0 + i, 0), field(m0 + i, nz + 1), pb};
-            if (p2p) { x[i].p_up = peer_field(1, m0 + i, 0); x[i].p_dn = peer_field(0, m0 + i, peer_lay[0].nz + 1); }
+            if (p2p) {      // into the neighbours' mailboxes: my top plane is "from below" up there, my plane 1 "from above" down there
+                x[i].p_up = copy_slot(peer_mail[1], peer_lay[1], kind, 0, i);
+                x[i].p_dn = copy_slot(peer_mail[0], peer_lay[0], kind, 1, i);
+            }
         }
-        return ring(x, 3, "ghost-plane copy");
+        int rc = ring(x, 3, "ghost-plane copy");
+        if (rc || !p2p) return rc;
+        UnpackArgs u{};
+        for (int i = 0; i < 3; ++i) {
+            u.src[i] = copy_slot(mail, lay, kind, 0, i); u.dst[i] = field(m0 + i, 0);
+            u.src[3 + i] = copy_slot(mail, lay, kind, 1, i); u.dst[3 + i] = field(m0 + i, nz + 1);
+        }
+        u.bytes = (long long)pb;
+        k_planes_unpack<<<dim3(8, 6), 256, 0, c->stream>>>(u);
+        ++c->launches;
+        return ctx(c->check_launch("k_planes_unpack"));
     }
     int slab_advance_b(double hx, double hy, double hz) {
         int rc;
@@ -672,6 +709,7 @@ int cpic_mgpu_create(const cpic_params* global, int32_t rank, int32_t world, con
         L.scratch = (long long)off; off = up256(off + (size_t)m->plane() * 12 * m->rb() * 2);
         L.recv_dn = (long long)off; off = up256(off + pb);
         L.recv_up = (long long)off; off = up256(off + pb);
+        L.copy = (long long)off; off = up256(off + 12 * m->copy_stride());
         L.bytes = (long long)off; L.send_cap = m->send_cap; L.nz = c->g.nz; L.plane = m->plane();
         { void* fp = nullptr; int64_t n_ = 0, stride = 0; c->device_ptr(16, &fp, &n_, &stride); L.nc_pad = stride; }
         if (cudaMalloc(&m->mail, off) != cudaSuccess) return bail(CPIC_E_NOMEM, "cudaMalloc(mailbox)");

@@ -14,12 +14,17 @@ from oracle.api import PARTICLE_NAMES, Restatement
 
 pytestmark = pytest.mark.gpu
 
-GRID, NPPC, NSTEPS = (12, 10, 16), 12, 7
+NPPC, NSTEPS = 12, 7
+
+
+def _grid():
+    """8 planes per slab: more than 1024 cells each, so that every rank runs k_push3 (and the graph path applies)"""
+    return (12, 10, 8 * max(2, _world()))
 
 
 def _world():
     import torch
-    return min(torch.cuda.device_count(), 2)
+    return min(torch.cuda.device_count(), int(os.environ.get("CPIC_TEST_WORLD", "2")))
 
 
 def _worker(rank, world, idfile, outdir, mode, graph):
@@ -28,7 +33,7 @@ def _worker(rank, world, idfile, outdir, mode, graph):
     import cabanapic_b200 as cp
     from cabanapic_b200 import _lib
     from test_dist import _split_state
-    nx, ny, nz = GRID
+    nx, ny, nz = _grid()
     s = random_state(nx, ny, nz, nppc=NPPC, prec="f32", seed=21)
     s.p["uz"] *= 0.5                                   # thermal anisotropy (C4: Weibel-type)
     k = cp.Consts(**consts_for(nx, ny, nz, "f32").to_dict())
@@ -89,7 +94,7 @@ def _run(tmp_path, mode, graph):
 
 
 def _oracle(world):
-    nx, ny, nz = GRID
+    nx, ny, nz = _grid()
     s = random_state(nx, ny, nz, nppc=NPPC, prec="f32", seed=21)
     s.p["uz"] *= 0.5
     k = consts_for(nx, ny, nz, "f32")
@@ -116,7 +121,7 @@ def _oracle(world):
 
 
 def _check_state(world, got, s, tol=5e-5, ftol=2e-4):
-    nx, ny, nz = GRID
+    nx, ny, nz = _grid()
     plane = (nx + 2) * (ny + 2)
     P = {n: np.concatenate([g["p_" + n] for g in got]) for n in PARTICLE_NAMES}
     assert len(P["cell"]) == s.np
