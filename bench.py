@@ -338,7 +338,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e and world == 1:
         e2e = runner.e2e(args.e2e_steps, sort_interval)
-    elif world > 1:
+    elif world > 1 and not args.no_e2e:
         e2e = runner.e2e(args.e2e_steps, sort_interval)
         if e2e is not None:
             t = torch.tensor([e2e["seconds"]], device="cuda", dtype=torch.float64)
@@ -530,9 +530,13 @@ def side_lines(device):
             m = re.search(r"#(\d+) steps of (\d+) particles in ([0-9.]+) s: ([0-9.e+]+) particle-steps/s", r.stdout)
             if not m:
                 raise RuntimeError("no summary line: " + (r.stdout[-200:] + r.stderr[-200:]))
+            m2 = re.search(r"#steady: (\d+) steps after the first .* in ([0-9.]+) s: ([0-9.e+]+) particle-steps/s", r.stdout)
             e = {"steps": int(m.group(1)), "particles": int(m.group(2)), "seconds": float(m.group(3)),
                  "value": float(m.group(4)), "unit": "particle-steps/s", "steps_per_s": int(m.group(1)) / float(m.group(3)),
                  "path": f"examples/build/{exe} (C++ facade over the C ABI, default settings, wall clock incl. launches)"}
+            if m2:      # without the first step, which carries the one-time upload of the host-initialised particles
+                e["steady_value"] = float(m2.group(3))
+                e["steady_steps_per_s"] = int(m2.group(1)) / max(float(m2.group(2)), 1e-9)
             if deck and RefLib.available(deck, "f32"):
                 R = RefLib(deck, "f32").create_from_deck(solver=0)
                 kk, _, _ = R.deck_consts()

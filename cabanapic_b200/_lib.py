@@ -152,6 +152,7 @@ def lib() -> C.CDLL:
             "cpic_mgpu_sync": [vp],
             "cpic_mgpu_used_graph": [vp],
             "cpic_mgpu_transport": [vp],
+            "cpic_mgpu_step_host": [vp, C.POINTER(Consts), C.POINTER(vp), C.POINTER(vp), i64, i64, C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)],
         }
         L.cpic_mgpu_last_error.restype = C.c_char_p
         L.cpic_mgpu_last_error.argtypes = [C.c_void_p]
@@ -181,7 +182,7 @@ EXPORTED = ["cpic_abi_version", "cpic_last_error", "cpic_create", "cpic_destroy"
 EXPORTED_MGPU = ["cpic_mgpu_last_error", "cpic_mgpu_unique_id", "cpic_mgpu_bootstrap_file", "cpic_mgpu_create",
                  "cpic_mgpu_destroy", "cpic_mgpu_context", "cpic_mgpu_layout", "cpic_mgpu_init_uniform_plasma",
                  "cpic_mgpu_reduce_accumulator", "cpic_mgpu_step", "cpic_mgpu_prepare_graph", "cpic_mgpu_migration_counts", "cpic_mgpu_last_migration",
-                 "cpic_mgpu_energies", "cpic_mgpu_state_digest", "cpic_mgpu_sync", "cpic_mgpu_used_graph", "cpic_mgpu_transport"]
+                 "cpic_mgpu_energies", "cpic_mgpu_state_digest", "cpic_mgpu_sync", "cpic_mgpu_used_graph", "cpic_mgpu_transport", "cpic_mgpu_step_host"]
 TRANSPORT_NAMES = {0: "none", 1: "nccl", 2: "peer-memory"}
 MGPU_REPLICATED, MGPU_SLAB, MGPU_AUTO = 0, 1, 2
 DIGEST_NAMES = ["particles", "weight_sum", "cells_not_interior", "offsets_out_of_range", "kinetic_energy",
@@ -525,6 +526,19 @@ class Mgpu:
 
     def step(self, k: Consts, nsteps=1, sort_interval=SORT_FUSED, use_graph=False):
         self._ck(self.L.cpic_mgpu_step(self.h, C.byref(k), nsteps, sort_interval, 1 if use_graph else 0))
+
+    def step_host(self, k: Consts, p_in, p_out, n, fields_in, fields_out):
+        """cpic_mgpu_step_host: p_in / p_out are dicts of host member arrays (p_out's at least as long as the count after
+        the step), fields_* (9, nc) host arrays; returns this rank's particle count after the step."""
+        names = "dx dy dz ux uy uz w cell".split()
+        pin = (C.c_void_p * 8)(*[p_in[m].ctypes.data for m in names])
+        pout = (C.c_void_p * 8)(*[p_out[m].ctypes.data for m in names])
+        fin = (C.c_void_p * 9)(*[fields_in[m].ctypes.data for m in range(9)])
+        fout = (C.c_void_p * 9)(*[fields_out[m].ctypes.data for m in range(9)])
+        cap = min(len(p_out[m]) for m in names)
+        n_out = C.c_int64()
+        self._ck(self.L.cpic_mgpu_step_host(self.h, C.byref(k), pin, pout, int(n), int(cap), C.byref(n_out), fin, fout))
+        return int(n_out.value)
 
     def prepare_graph(self, k: Consts):
         """capture the pair-of-steps graph now (nothing executes); False when the graph path does not apply"""

@@ -112,6 +112,11 @@ struct CtxBase {
     bool dev_count = false;         // slab mode: np lives in dc[0] on the device, the host's np is stale
     virtual int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
                           const void* const fin[9], void* const fout[9], double* energies) = 0;
+    // the two halves of a host-resident step that the multi-GPU layer weaves its exchanges between (cpic_mgpu_step_host)
+    virtual int host_push_phase(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
+                                const void* const fin[9], bool slab) = 0;
+    virtual int host_patch_phase(void* const out[8], long long n_in, long long out_capacity, long long* n_out) = 0;
+    virtual int host_fields_out(void* const fout[9]) = 0;
     virtual double* energy_scratch() = 0;
     virtual unsigned long long* stats_dev() = 0;
 };
@@ -354,7 +359,7 @@ struct Ctx final : CtxBase {
     long long leave_cap = 0;
     // (re)arm the leaver list for a push in slab mode; no-op while z is periodic inside this context
     int arm_leave_list(PushArgs<R>& a) {
-        a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0;
+        a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0; a.leave_off = 0;
         leavers_valid = false;
         if ((g.per & 4) || prm.boundary != CPIC_BOUNDARY_PERIODIC || !ghost_clean) return CPIC_OK;
         int rc;
@@ -870,7 +875,7 @@ struct Ctx final : CtxBase {
         a.stats = stats;
         a.hist = nullptr;
         a.dst = P[cur]; a.cursor = nullptr;
-        a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0;
+        a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0; a.leave_off = 0;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         a.np_dev = nullptr;
         a.priv_nc = use_priv() ? (int)g.nc : 0;
@@ -948,10 +953,15 @@ struct Ctx final : CtxBase {
             if ((rc = cuda(cudaMalloc(&b, (size_t)hs_cap * (7 * sizeof(R) + sizeof(int))), "cudaMalloc(host-step staging)"))) return rc;
         return CPIC_OK;
     }
-    int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
-                  const void* const fin[9], void* const fout[9], double* energies) override {
+    // First half of a host-resident step: fields up, interpolators, then the particles streamed through the device chunk
+    // by chunk (H2D / pack / in-place push / unpack / D2H on three streams).  slab: z is open -- the leavers stay in the
+    // store (and in `out`, to be patched by host_patch_phase) with their store indices listed for the migration, and a
+    // particle arriving from the host in a z ghost plane counts as a bad cell.
+    int host_push_phase(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
+                        const void* const fin[9], bool slab) override {
         if (n < 0 || n > cap) return fail(CPIC_E_CAPACITY, "step_host: %lld particles exceed capacity %lld", n, cap);
         int rc;
+        if (dev_count && (rc = sync_np())) return rc;
         if ((rc = ensure_host_stream())) return rc;
         rec(6);
         // fields first: the interpolators every chunk's push gathers from (example/example.cpp:233-236)
@@ -964,6 +974,12 @@ struct Ctx final : CtxBase {
         np = n;
         hist_valid = false; cursor_valid = false; seg_valid = false; leavers_valid = false; ghost_clean = false; want_hist = false;
         PushArgs<R> a0 = push_args(k);
+        const long long plane = (long long)g.gx * g.gy;
+        const long long c_lo = slab ? plane : 0, c_hi = slab ? (long long)(g.nz + 1) * plane : g.nc;
+        if (slab) {      // every particle is checked to lie in an interior plane below: the ghost planes are empty
+            ghost_clean = true;
+            if ((rc = arm_leave_list(a0))) return rc;
+        }
         const int32_t* cin = static_cast<const int32_t*>(in[7]);
         long long chunk = 0;
         for (long long first = 0; first < n; first += hs_cap, ++chunk) {
@@ -978,11 +994,12 @@ struct Ctx final : CtxBase {
             cudaEventRecord(hs_ev[0 + b], hs_up);
             // records, push (src/push.h + src/move_p.h on this chunk), members
             cudaStreamWaitEvent(stream, hs_ev[0 + b], 0);
-            k_pack_records_checked<R><<<blocks_for(cn), 256, 0, stream>>>(P[cur], first, up, cn, g.nc, bad);
+            k_pack_records_checked<R><<<blocks_for(cn), 256, 0, stream>>>(P[cur], first, up, cn, c_lo, c_hi, bad);
             if ((rc = check_launch("k_pack_records_checked"))) return rc;
             cudaEventRecord(hs_ev[2 + b], stream);
             PushArgs<R> a = a0;
             a.p.rec = P[cur].rec + first; a.dst = a.p; a.np = cn;
+            a.leave_off = (unsigned)first;      // the leaver list holds indices of the whole store
             if ((rc = launch_inplace(a))) return rc;
             if (out) {
                 if (chunk >= 2) cudaStreamWaitEvent(stream, hs_ev[6 + b], 0);
@@ -996,6 +1013,81 @@ struct Ctx final : CtxBase {
                 cudaEventRecord(hs_ev[6 + b], hs_dn);
             }
         }
+        return CPIC_OK;
+    }
+    int host_fields_out(void* const fout[9]) override {
+        int rc;
+        if (fout)
+            for (int m = 0; m < F_N; ++m)
+                if (fout[m] && (rc = cuda(cudaMemcpyAsync(fout[m], fields + (long long)m * nc_pad, (size_t)g.nc * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H fields"))) return rc;
+        return CPIC_OK;
+    }
+    // Second half in slab mode, after the migration: the device store is final; `out` holds what the chunks downloaded
+    // before it.  Patch it: the holes the leavers left (filled from the store's tail by the extraction) and the range the
+    // arrivals were appended to.  Synchronises.
+    int host_patch_phase(void* const out[8], long long n_in, long long out_capacity, long long* n_out) override {
+        int rc;
+        unsigned hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long hd[4] = {0, 0, 0, 0};
+        if (!dev_count || !mig_counters) return fail(CPIC_E_INVALID, "step_host: no device-counted migration preceded the patch");
+        if ((rc = cuda(cudaMemcpyAsync(hc, mig_counters, sizeof hc, cudaMemcpyDeviceToHost, stream), "D2H migration counters"))) return rc;
+        if ((rc = cuda(cudaMemcpyAsync(hd, dc, sizeof hd, cudaMemcpyDeviceToHost, stream), "D2H counts"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(hs_dn), "step_host (D2H)"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(hs_up), "step_host (H2D)"))) return rc;
+        unsigned nbad = 0;
+        if ((rc = cuda(cudaMemcpyAsync(&nbad, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
+        if ((rc = sync_np())) return rc;      // (synchronises; reports overflows of the migration)
+        if (nbad) { np = 0; return fail(CPIC_E_BAD_CELL, "step_host: %u particles lie outside the slab's interior planes", nbad); }
+        const long long n_after = n_in - hd[2] - hd[3], n_final = np, nh = hc[3];
+        if (n_out) *n_out = n_final;
+        rec(7);
+        ev_valid[3] = true;
+        if (!out) return CPIC_OK;
+        if (n_final > out_capacity) return fail(CPIC_E_CAPACITY, "step_host: %lld particles after the migration exceed the output capacity %lld", n_final, out_capacity);
+        // (a) arrivals: the store range [n_after, n_final)
+        for (long long first = n_after; first < n_final; first += hs_cap) {
+            const long long cn = std::min(hs_cap, n_final - first);
+            SendBuf<R> dn = carve_sendbuf<R>(hs_buf[2], hs_cap);
+            k_unpack_records<R><<<blocks_for(cn), 256, 0, stream>>>(P[cur], first, dn, cn);
+            if ((rc = check_launch("k_unpack_records"))) return rc;
+            for (int m = 0; m < 7; ++m)
+                if (out[m] && (rc = cuda(cudaMemcpyAsync((R*)out[m] + first, dn.m[m], (size_t)cn * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H arrivals"))) return rc;
+            if (out[7] && (rc = cuda(cudaMemcpyAsync((int32_t*)out[7] + first, dn.cell, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H arrivals"))) return rc;
+            if ((rc = cuda(cudaStreamSynchronize(stream), "step_host (arrivals)"))) return rc;
+        }
+        // (b) holes: positions mig_lists[0 .. nh) now hold particles moved in from the tail
+        std::vector<unsigned> idx;
+        std::vector<char> rec_host;
+        for (long long j0 = 0; j0 < nh; j0 += hs_cap) {
+            const long long cn = std::min(hs_cap, nh - j0);
+            SendBuf<R> dn = carve_sendbuf<R>(hs_buf[2], hs_cap);
+            k_gather_records<R><<<blocks_for(cn), 256, 0, stream>>>(P[cur], mig_lists + j0, dn, cn);
+            if ((rc = check_launch("k_gather_records"))) return rc;
+            idx.resize((size_t)cn);
+            rec_host.resize((size_t)cn * (7 * sizeof(R) + sizeof(int)));
+            if ((rc = cuda(cudaMemcpyAsync(idx.data(), mig_lists + j0, (size_t)cn * sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H hole list"))) return rc;
+            for (int m = 0; m < 7; ++m)
+                if ((rc = cuda(cudaMemcpyAsync(rec_host.data() + (size_t)m * cn * sizeof(R), dn.m[m], (size_t)cn * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H patches"))) return rc;
+            if ((rc = cuda(cudaMemcpyAsync(rec_host.data() + (size_t)7 * cn * sizeof(R), dn.cell, (size_t)cn * sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H patches"))) return rc;
+            if ((rc = cuda(cudaStreamSynchronize(stream), "step_host (patches)"))) return rc;
+            for (int m = 0; m < 7; ++m) {
+                if (!out[m]) continue;
+                R* o = static_cast<R*>(out[m]);
+                const R* v = reinterpret_cast<const R*>(rec_host.data() + (size_t)m * cn * sizeof(R));
+                for (long long j = 0; j < cn; ++j) o[idx[(size_t)j]] = v[j];
+            }
+            if (out[7]) {
+                int32_t* o = static_cast<int32_t*>(out[7]);
+                const int32_t* v = reinterpret_cast<const int32_t*>(rec_host.data() + (size_t)7 * cn * sizeof(R));
+                for (long long j = 0; j < cn; ++j) o[idx[(size_t)j]] = v[j];
+            }
+        }
+        return CPIC_OK;
+    }
+    int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
+                  const void* const fin[9], void* const fout[9], double* energies) override {
+        int rc;
+        if ((rc = host_push_phase(k, in, out, n, fin, false))) return rc;
         // field side of the step (example/example.cpp:248-266); the last chunks' D2H overlaps it
         const double hx = sizeof(R) == 4 ? (double)(0.5f * (float)k.px) : 0.5 * k.px;
         const double hy = sizeof(R) == 4 ? (double)(0.5f * (float)k.py) : 0.5 * k.py;
@@ -1009,9 +1101,7 @@ struct Ctx final : CtxBase {
             if ((rc = energies_async(en_dev))) return rc;
             if ((rc = cuda(cudaMemcpyAsync(h, en_dev, sizeof h, cudaMemcpyDeviceToHost, stream), "D2H energies"))) return rc;
         }
-        if (fout)
-            for (int m = 0; m < F_N; ++m)
-                if (fout[m] && (rc = cuda(cudaMemcpyAsync(fout[m], fields + (long long)m * nc_pad, (size_t)g.nc * sizeof(R), cudaMemcpyDeviceToHost, stream), "D2H fields"))) return rc;
+        if ((rc = host_fields_out(fout))) return rc;
         unsigned nbad = 0;
         if ((rc = cuda(cudaMemcpyAsync(&nbad, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
         rec(7);

@@ -547,6 +547,24 @@ struct Mgpu {
         if ((rc = slab_advance_e(k))) return rc;
         return slab_advance_b(hx, hy, hz);
     }
+    // One step for a caller whose slab lives in HOST memory: the particles stream through the device chunk by chunk
+    // (H2D / in-place push / D2H overlapped, Ctx::host_push_phase), then the usual exchanges and the field side, then the
+    // host copy is patched where the migration changed the store (holes filled from the tail, arrivals appended).
+    int slab_step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n, long long out_cap,
+                       long long* n_out, const void* const fin[9], void* const fout[9]) {
+        int rc;
+        double hx, hy, hz;
+        halves(k, hx, hy, hz);
+        if ((rc = ctx(c->host_push_phase(k, in, out, n, fin, true)))) return rc;
+        if ((rc = exchange_accumulators(true))) return rc;
+        if ((rc = ctx(c->unload_accumulator(k)))) return rc;
+        if ((rc = slab_advance_b(hx, hy, hz))) return rc;
+        if ((rc = slab_advance_e(k))) return rc;
+        if ((rc = slab_advance_b(hx, hy, hz))) return rc;
+        if ((rc = ctx(c->host_fields_out(fout)))) return rc;
+        if ((rc = ctx(c->host_patch_phase(out, n, out_cap, n_out)))) return rc;
+        return check_p2p();
+    }
     int replicated_step(const cpic_consts& k, bool sort, bool fused) {
         int rc;
         double hx, hy, hz;
@@ -816,6 +834,24 @@ int cpic_mgpu_step(cpic_mgpu* mm, const cpic_consts* k, int64_t nsteps, int32_t 
         rc = m->replicated_step(*k, sort, fused);
     }
     m->steps_done += nsteps;
+    return rc;
+}
+
+int cpic_mgpu_step_host(cpic_mgpu* mm, const cpic_consts* k, const void* const in[8], void* const out[8], int64_t n,
+                        int64_t out_capacity, int64_t* n_out, const void* const fields_in[9], void* const fields_out[9]) {
+    MGPU_OR_FAIL(mm);
+    if (!k || !in || !fields_in || n < 0) return m->fail(CPIC_E_INVALID, "mgpu_step_host: bad arguments");
+    for (int f = 0; f < 9; ++f) if (!fields_in[f]) return m->fail(CPIC_E_INVALID, "mgpu_step_host: null field member %d", f);
+    if (n > 0) for (int f = 0; f < 8; ++f) if (!in[f]) return m->fail(CPIC_E_INVALID, "mgpu_step_host: null particle member %d", f);
+    CtxBase* c = m->c;
+    if (m->mode != CPIC_MGPU_SLAB) return m->fail(CPIC_E_UNSUPPORTED, "mgpu_step_host: slab mode only");
+    m->used_graph = false;
+    long long no = n;
+    int rc;
+    if (c->g.per & 4) rc = m->ctx(c->step_host(*k, in, out, n, fields_in, fields_out, nullptr));      // one periodic slab: the single-GPU path
+    else rc = m->slab_step_host(*k, in, out, n, out_capacity, &no, fields_in, fields_out);
+    if (!rc && n_out) *n_out = no;
+    if (!rc) m->steps_done += 1;
     return rc;
 }
 

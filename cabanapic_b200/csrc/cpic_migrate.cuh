@@ -228,19 +228,30 @@ __global__ void __launch_bounds__(256) k_pack_records(Particles<R> p, long long 
     r.mom.x = b.m[3][j]; r.mom.y = b.m[4][j]; r.mom.z = b.m[5][j]; r.mom.w = b.m[6][j];
     p.rec[first + j] = r;
 }
-// k_pack_records for data arriving from the host: a cell index outside [0, nc) is counted in *bad and stored
-// as cell 0 (a ghost cell), so that a push of the chunk before the host has seen the count stays in bounds.
+// k_pack_records for data arriving from the host: a cell index outside [lo, hi) -- the whole grid, or a slab's interior
+// planes -- is counted in *bad and stored as cell lo (a ghost / edge cell inside the grid), so that a push of the chunk
+// before the host has seen the count stays in bounds.
 template <class R>
 __global__ void __launch_bounds__(256) k_pack_records_checked(Particles<R> p, long long first, SendBuf<R> b, long long n,
-                                                              long long nc, unsigned* __restrict__ bad) {
+                                                              long long lo, long long hi, unsigned* __restrict__ bad) {
     const long long j = blockIdx.x * 256LL + threadIdx.x;
     if (j >= n) return;
     int c = b.cell[j];
-    if (c < 0 || c >= nc) { atomicAdd(bad, 1u); c = 0; }
+    if (c < lo || c >= hi) { atomicAdd(bad, 1u); c = (int)lo; }
     PRec<R> r;
     r.pos.x = b.m[0][j]; r.pos.y = b.m[1][j]; r.pos.z = b.m[2][j]; r.pos.w = cell_to_real(c, R(0));
     r.mom.x = b.m[3][j]; r.mom.y = b.m[4][j]; r.mom.z = b.m[5][j]; r.mom.w = b.m[6][j];
     p.rec[first + j] = r;
+}
+// records at listed store positions -> member arrays (the patches of cpic_mgpu_step_host)
+template <class R>
+__global__ void __launch_bounds__(256) k_gather_records(Particles<R> p, const unsigned* __restrict__ list, SendBuf<R> b, long long n) {
+    const long long j = blockIdx.x * 256LL + threadIdx.x;
+    if (j >= n) return;
+    const PRec<R> r = p.rec[list[j]];
+    b.m[0][j] = r.pos.x; b.m[1][j] = r.pos.y; b.m[2][j] = r.pos.z;
+    b.m[3][j] = r.mom.x; b.m[4][j] = r.mom.y; b.m[5][j] = r.mom.z; b.m[6][j] = r.mom.w;
+    b.cell[j] = real_to_cell(r.pos.w);
 }
 template <class R>
 __global__ void __launch_bounds__(256) k_unpack_records(Particles<R> p, long long first, SendBuf<R> b, long long n) {

@@ -46,6 +46,7 @@ struct PushArgs {
     unsigned* leave_list;     // optional
     unsigned* leave_count;
     unsigned leave_cap;
+    unsigned leave_off;        // added to the listed indices (a push over a sub-range of the store: cpic_step_host)
     int leave_lo, leave_hi;
     int priv_nc;               // > 0: k_push2<PRIV> keeps a block-private accumulator (+ histogram) of this many cells in shared memory
     const long long* np_dev;   // optional: the particle count lives on the device (overrides np; k_push2 only)
@@ -419,7 +420,7 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
             if (lane == 0) base = atomicAdd(a.leave_count, (unsigned)__popc(lm));
             base = __shfl_sync(0xffffffffu, base, 0);
             const unsigned j = base + __popc(lm & ((1u << lane) - 1u));
-            if (leaves && j < a.leave_cap) a.leave_list[j] = leaver;
+            if (leaves && j < a.leave_cap) a.leave_list[j] = leaver + a.leave_off;
         }
     }
 }

@@ -244,7 +244,7 @@ __device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, const Mo
             if (lane == 0) base = atomicAdd(a.leave_count, (unsigned)__popc(lm));
             base = __shfl_sync(0xffffffffu, base, 0);
             const unsigned j = base + __popc(lm & ((1u << lane) - 1u));
-            if (leaves && j < a.leave_cap) a.leave_list[j] = leaver;
+            if (leaves && j < a.leave_cap) a.leave_list[j] = leaver + a.leave_off;
         }
     }
 }

@@ -87,6 +87,17 @@ int  cpic_mgpu_step(cpic_mgpu* m, const cpic_consts* k, int64_t nsteps, int32_t 
  * otherwise captures on its first eligible call.  Returns CPIC_E_UNSUPPORTED when the graph path does not apply. */
 int  cpic_mgpu_prepare_graph(cpic_mgpu* m, const cpic_consts* k);
 
+/* One step for a caller whose slab lives in HOST memory (every array of the reference's host build does,
+ * example/example.cpp:58-113) -- cpic_step_host for the slab mode.  in[8] / out[8]: this rank's particle members
+ * (dx dy dz ux uy uz w cell, cell indices in this slab's numbering, interior planes only), n of them; fields_in[9] /
+ * fields_out[9]: this slab's field members incl. ghosts.  The particles stream through the device in chunks (H2D of
+ * chunk i+1, in-place push of chunk i, D2H of chunk i-1 overlap), the ghost-plane / leaver exchanges and the field
+ * advance follow, and `out` is then patched where the migration changed the store: holes left by the leavers are
+ * filled from the tail, arrivals appended.  *n_out = this rank's particle count after the step (<= out_capacity).
+ * Particle order is the caller's otherwise.  SLAB mode only. */
+int  cpic_mgpu_step_host(cpic_mgpu* m, const cpic_consts* k, const void* const in[8], void* const out[8], int64_t n,
+                         int64_t out_capacity, int64_t* n_out, const void* const fields_in[9], void* const fields_out[9]);
+
 /* Particles this rank sent to its lower / upper neighbour since creation (SLAB; synchronises). */
 int  cpic_mgpu_migration_counts(cpic_mgpu* m, int64_t out[2]);
 /* ... and in the last step only. */

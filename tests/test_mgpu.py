@@ -56,7 +56,23 @@ def _worker(rank, world, idfile, outdir, mode, graph):
     m.ctx.upload_fields(lf)
     transport = m.transport
     mig, en = [], []
-    if graph:                                          # whole run in two calls: eager warm-up, then graph replay
+    if graph == "host":                                # the slab lives in host memory: cpic_mgpu_step_host per step
+        capn = 3 * len(p["cell"]) + 64
+        a = {n: np.zeros(capn, dtype=p[n].dtype) for n in PARTICLE_NAMES}
+        b = {n: np.zeros(capn, dtype=p[n].dtype) for n in PARTICLE_NAMES}
+        cnt = len(p["cell"])
+        for n in PARTICLE_NAMES:
+            a[n][:cnt] = p[n]
+        fa, fb = np.ascontiguousarray(lf, dtype=np.float32).copy(), np.zeros_like(lf, dtype=np.float32)
+        used = False
+        for _ in range(NSTEPS):
+            cnt = m.step_host(k, a, b, cnt, fa, fb)
+            mig.append(m.last_migration())
+            a, b, fa, fb = b, a, fb, fa
+        assert m.ctx.num_particles == cnt
+        host_p = {n: a[n][:cnt].copy() for n in PARTICLE_NAMES}
+        host_f = fa.copy()
+    elif graph:                                          # whole run in two calls: eager warm-up, then graph replay
         m.step(k, 3, cp.SORT_FUSED, use_graph=True)
         m.step(k, NSTEPS - 3, cp.SORT_FUSED, use_graph=True)
         used = m.used_graph
@@ -69,8 +85,14 @@ def _worker(rank, world, idfile, outdir, mode, graph):
     dg = m.state_digest()
     tot = m.migration_counts()
     out = m.ctx.download_particles()
-    out["cell"] = out["cell"] + z0 * (nx + 2) * (ny + 2)
     f = m.ctx.download_fields()
+    if graph == "host":                                # the host copy IS the result; it must also equal the device's state
+        og, oo = canonical_order(host_p), canonical_order(out)
+        for n in PARTICLE_NAMES:
+            assert np.array_equal(host_p[n][og], out[n][oo]), n
+        assert np.array_equal(host_f, f)
+        out = host_p
+    out["cell"] = out["cell"] + z0 * (nx + 2) * (ny + 2)
     m.close()
     np.savez(os.path.join(outdir, f"r{rank}.npz"), f=f, mig=np.array(mig), en=np.array(en), z0=z0, nzl=nzl, used=used, transport=transport,
              digest=np.array([dg[n] for n in _lib.DIGEST_NAMES]), tot=np.array(tot), **{"p_" + n: out[n] for n in PARTICLE_NAMES})
@@ -160,6 +182,21 @@ def test_native_slab_stepper_graph_replay(tmp_path):
     s, want_mig, _ = _oracle(world)
     assert bool(got[0]["used"]), "the graph path was not taken"
     for r in range(world):
+        assert np.array_equal(got[r]["tot"], want_mig[r].sum(axis=0))
+    _check_state(world, got, s)
+
+
+def test_native_slab_step_host_matches_oracle(tmp_path, monkeypatch):
+    """cpic_mgpu_step_host: every rank keeps its slab in host arrays; per step the particles stream through the GPU in
+    chunks (several per step here: CPIC_HOST_CHUNK), the exchanges and the field advance follow, and the host copy is
+    patched where the migration changed the store.  Same bars as the device-resident stepper: migration counts per
+    (step, face) bit-exact against the oracle, cells bit-exact, state / fields to summation order; the host copy equals
+    the device store."""
+    monkeypatch.setenv("CPIC_HOST_CHUNK", "1024")
+    world, got = _run(tmp_path, "slab", graph="host")
+    s, want_mig, _ = _oracle(world)
+    for r in range(world):
+        assert np.array_equal(got[r]["mig"], want_mig[r]), (r, got[r]["mig"], want_mig[r])
         assert np.array_equal(got[r]["tot"], want_mig[r].sum(axis=0))
     _check_state(world, got, s)
 
