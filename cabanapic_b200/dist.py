@@ -784,12 +784,15 @@ class NativeBench:
             return None
         names = "dx dy dz ux uy uz w".split()
         cap2 = int(n * 1.05) + 1024                       # the count drifts by the net migration
-        host = {m: torch.empty(cap2, dtype=torch.float32, pin_memory=True).numpy() for m in names}
-        host["cell"] = torch.empty(cap2, dtype=torch.int32, pin_memory=True).numpy()
-        back = {m: torch.empty(cap2, dtype=torch.float32, pin_memory=True).numpy() for m in names}
-        back["cell"] = torch.empty(cap2, dtype=torch.int32, pin_memory=True).numpy()
-        hf = torch.empty((9, c.nc), dtype=torch.float32, pin_memory=True).numpy()
-        hf2 = torch.empty((9, c.nc), dtype=torch.float32, pin_memory=True).numpy()
+        # the host arrays of a rank belong on the NUMA node its GPU hangs off (what numactl / the MPI launcher of a real
+        # run would arrange): pin this process to the GPU's CPU set while the pinned buffers are allocated and touched
+        old_aff = _bind_to_gpu_cpus(self.local) if self.world > 1 else None
+        host = {m: torch.zeros(cap2, dtype=torch.float32, pin_memory=True).numpy() for m in names}
+        host["cell"] = torch.zeros(cap2, dtype=torch.int32, pin_memory=True).numpy()
+        back = {m: torch.zeros(cap2, dtype=torch.float32, pin_memory=True).numpy() for m in names}
+        back["cell"] = torch.zeros(cap2, dtype=torch.int32, pin_memory=True).numpy()
+        hf = torch.zeros((9, c.nc), dtype=torch.float32, pin_memory=True).numpy()
+        hf2 = torch.zeros((9, c.nc), dtype=torch.float32, pin_memory=True).numpy()
         L = c.L
         up = [host[m].ctypes.data_as(C.c_void_p) for m in names] + [host["cell"].ctypes.data_as(C.c_void_p)]
         fptr = (C.c_void_p * 9)(*[hf[m].ctypes.data for m in range(9)])
@@ -821,6 +824,9 @@ class NativeBench:
             dist.barrier()
         torch.cuda.synchronize()
         sec = time.perf_counter() - t0
+        if old_aff is not None:
+            import os
+            os.sched_setaffinity(0, old_aff)
         what = ("per step and rank: ONE cpic_mgpu_step_host call on pinned host arrays (this slab's 8 particle members + 9 field "
                 "components in, the same out): chunked H2D / in-place push / D2H pipeline, peer-memory exchanges, field "
                 "advance, host copy patched for the migration; bytes summed over ranks") if streamed else (
@@ -828,10 +834,33 @@ class NativeBench:
                 "bytes summed over ranks")
         return {"value": self.d.num_particles * steps / sec, "unit": "particle-steps/s",
                 "h2d_bytes_per_step": nbytes * self.world, "d2h_bytes_per_step": nbytes * self.world,
-                "steps": steps, "seconds": sec, "what": what}
+                "steps": steps, "seconds": sec, "what": what, "host_buffers_numa_local": old_aff is not None}
 
     def close(self):
         self.m.close()
+
+
+def _bind_to_gpu_cpus(local):
+    """Restrict this process to the CPUs NVML reports as local to GPU `local` (its NUMA node); returns the previous
+    affinity set, or None when that is not possible."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus or cpus == old:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
 
 
 def make_runner(d, k, we, rank, world, local, mode="auto", fp_mode=_lib.FP_STRICT, native=True):
