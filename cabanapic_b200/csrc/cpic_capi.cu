@@ -783,9 +783,6 @@ struct Ctx final : CtxBase {
             q.ch = p3_ch; q.cpp = p3_cpp; q.gz = g.gz; q.plane = g.gx * g.gy; q.yblock = p3_yblock;
             q.nchunks = p3_cpp * g.gz; q.nc = (int)g.nc;
             q.work = work3;
-#if PUSH3_KO
-            q.ko = getenv("CPIC_KO") ? atoi(getenv("CPIC_KO")) : 0;
-#endif
             if (want_stats) cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), stream);
             rec(0);
             const bool fma = prm.fp_mode == CPIC_FP_CONTRACT;

@@ -26,14 +26,16 @@
 
 namespace cpic {
 
+// Block shape: 5 warps x 4 CTAs per SM = 20 warps at 96 registers.  Measured (profiles/r2_push3_block_shapes.log, 256x256x64 x
+// 64 ppc, ms): 5x4 5.71 | 10x2 5.83 | 12x2 5.96 | 4x4 5.98 | 4x5 6.00 | 8x2 6.05 | 6x3 6.15 | 8x3 6.16 (round-2 start) |
+// 20x1 6.19 | 11x2 6.20 | 3x6 6.22 | 9x2 6.25 | 16x1 6.38 | 7x3 6.51.  What helps: 96 instead of 80 registers (no loop
+// counter / pointer re-materialisation, 20 instead of 48 bytes of spill), a warp count per SM divisible by the four
+// schedulers, and small CTAs (the chunk barriers and the TMA wait stall fewer warps).
 #ifndef PUSH3_NWARPS
-#define PUSH3_NWARPS 8
+#define PUSH3_NWARPS 5
 #endif
 #ifndef PUSH3_MIN_BLOCKS
-#define PUSH3_MIN_BLOCKS 3
-#endif
-#ifndef PUSH3_KO
-#define PUSH3_KO 0
+#define PUSH3_MIN_BLOCKS 4
 #endif
 constexpr int PUSH3_WARPS = PUSH3_NWARPS;
 constexpr int PUSH3_CH_MAX = 264;      // cells per chunk (one x-row of the 256^3 deck incl. ghosts = 258)
@@ -49,11 +51,7 @@ struct Push3Args {
     // traffic lies between them at 256^3 x 64)
     int ch, cpp, gz, plane, yblock, nchunks, nc;
     unsigned* work;          // dynamic work counter (zeroed by the host before the launch)
-#if PUSH3_KO
-    int ko;                  // developer knock-outs (wrong results, timing only): see tools/r2_ko.sh
-#endif
 };
-
 
 // A warp's list of cell-crossers waiting for the drain (the in-kernel form of VPIC's particle_mover_t list the reference
 // kept in comments, src/push.h:271-291): 48-byte entries {x y z cell | rx ry rz slot | ux uy uz w}, three 128-bit words --
@@ -117,28 +115,6 @@ __device__ __forceinline__ void red_add_u32_if(bool p, unsigned* addr, unsigned 
                  : "memory");
 }
 
-#ifndef PUSH3_DUAL
-#define PUSH3_DUAL 0
-#endif
-#ifndef PUSH3_LATEPF
-#define PUSH3_LATEPF 0
-#endif
-// One 128-bit piece of an interpolator record: from the TMA-staged chunk (shared memory) or, for a foreigner whose cell
-// lies outside the chunk, from global memory -- no generic addressing (a generic pointer costs S2R SR_SWINHI / CgaCtaId
-// and 64-bit address arithmetic per tile).  The shared-memory load is unconditional (an out-of-chunk lane reads the
-// chunk's first record and discards it): a pair of complementary predicated loads makes ptxas treat the destination as
-// read-modify-write and spill it.
-template <int OFF>
-__device__ __forceinline__ float4 ld_interp(bool in, unsigned saddr, const float* gptr) {
-    float4 v;      // (not volatile: the address depends on this tile's records, which are loaded behind the chunk's barrier)
-    asm("{\n.reg .pred p;\nsetp.eq.u32 p, %6, 0;\n"
-        "ld.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %7];\n"
-        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5 + %7];\n}\n"
-        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-        : "r"(saddr), "l"(gptr), "r"((unsigned)in), "n"(OFF));
-    return v;
-}
-
 // Branch-free segmented sum of the warp's 32 deposit rows (see segsum_rows): lane -> (row group rg, entry group eg).
 // Rows of a tile's native stayers are sorted by cell; a row with cell -1 holds exact zeros and never breaks a run.
 // Lanes 24..31 count the native stayers per cell the same way (histogram of the new cells).
@@ -188,7 +164,7 @@ __device__ __forceinline__ void segsum_rows3(const float* rows, const int* rcell
 // mover's whole record at the slot the main path claimed for it.
 template <bool FMA, bool STATS>
 __device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, const MoverList3& ml, int first, int count, int lane,
-                                              unsigned long long& n_cross, unsigned long long (&n_wrap)[6], int ko = 0) {
+                                              unsigned long long& n_cross, unsigned long long (&n_wrap)[6]) {
     const int m = first + lane;
     bool leaves = false;
     unsigned leaver = 0;
@@ -204,7 +180,7 @@ __device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, const Mo
             const int axis = mover_streak(px, py, pz, dx, dy, dz, qq, sx, sy, sz, mx, my, mz, v5, dirv);
             float jc[12];
             streak_currents<FMA>(qq, sx, sy, sz, mx, my, mz, v5, jc);
-            if (!(PUSH3_KO && (ko & 64))) row_add_vec(a.acc + (long long)c * 12, jc);
+            row_add_vec(a.acc + (long long)c * 12, jc);
             if (axis == 3) break;
             const int code = cross_face(c, axis, dirv, a);
             if (code & CROSS_REFLECTED) {      // reflecting wall (Boundary::Reflect): stay on the face, turn around
@@ -231,10 +207,8 @@ __device__ __forceinline__ void drain_movers3(const PushArgs<float>& a, const Mo
         if (flip & 1u) o.mom.x = -o.mom.x;
         if (flip & 2u) o.mom.y = -o.mom.y;
         if (flip & 4u) o.mom.z = -o.mom.z;
-        if (!(PUSH3_KO && (ko & 128))) {
-            a.dst.rec[pn] = o;
-            atomicAdd(a.hist + c, 1u);
-        }
+        a.dst.rec[pn] = o;
+        atomicAdd(a.hist + c, 1u);
     }
     __syncwarp();
     if (a.leave_list) {      // slab mode: list the particles left in a z ghost plane, one counter atomic per warp
@@ -259,11 +233,6 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
     const int warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     MoverList3& ml = sm.lists[warp];
-#if PUSH3_KO
-    const int ko = q.ko;
-#else
-    constexpr int ko = 0;
-#endif
     float* rows = sm.rows[warp];
     int* rcell = sm.rcell[warp];
     int* rcnt = sm.rcnt[warp];
@@ -336,25 +305,15 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             const unsigned iA = i0 + 2u * lane, iB = iA + 1u;
             const bool validA = iA < r1, validB = iB < r1;
             PRec<float> rA_n = rzero, rB_n = rzero;
-#if !PUSH3_LATEPF
             {   // the next tile's records: requested now, consumed next iteration (nothing may touch them before)
                 const unsigned nA = iA + 64u;
                 if (nA < r1) rA_n = grec[nA];
                 if (nA + 1u < r1) rB_n = grec[nA + 1u];
             }
-#endif
             const int cA = validA ? real_to_cell(rA.pos.w) : c0;
             const int cB = validB ? real_to_cell(rB.pos.w) : cA;
             const unsigned oA = (unsigned)(cA - c0), oB = (unsigned)(cB - c0);
-            bool inA = oA < (unsigned)chn, inB = oB < (unsigned)chn;
-#if PUSH3_KO
-            unsigned oA_ = oA, oB_ = oB;
-            if (ko & 16) { if (!inA) oA_ = 0; if (!inB) oB_ = 0; }
-            const bool ginA = inA || (ko & 16), ginB = inB || (ko & 16);
-#else
-            const unsigned oA_ = oA, oB_ = oB;
-            const bool ginA = inA, ginB = inB;
-#endif
+            const bool inA = oA < (unsigned)chn, inB = oB < (unsigned)chn;
             // native: the particle's index lies inside the segment of its own cell
             bool natA = false, natB = false;
             if (validA && inA) { const unsigned lo = sS[oA]; natA = (iA - lo) < (sS[oA + 1] - lo); }
@@ -378,11 +337,9 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             // destination slots (in the segment of the cell the particle is in now); the atomics' round trip overlaps
             // the gather and the Boris rotation
             unsigned base = 0, fsA = 0, fsB = 0;
-            if (!(PUSH3_KO && (ko & 32))) {
-                if (mycnt) base = atomicAdd(a.cursor + cf + lane, mycnt);
-                if (forA) fsA = atomicAdd(a.cursor + cA, 1u);
-                if (forB) fsB = atomicAdd(a.cursor + cB, 1u);
-            } else { base = iA; fsA = iA; fsB = iB; }
+            if (mycnt) base = atomicAdd(a.cursor + cf + lane, mycnt);
+            if (forA) fsA = atomicAdd(a.cursor + cA, 1u);
+            if (forB) fsB = atomicAdd(a.cursor + cB, 1u);
 
             float2 x = make_float2(rA.pos.x, rB.pos.x), y = make_float2(rA.pos.y, rB.pos.y), z = make_float2(rA.pos.z, rB.pos.z);
             float2 ux = make_float2(rA.mom.x, rB.mom.x), uy = make_float2(rA.mom.y, rB.mom.y), uz = make_float2(rA.mom.z, rB.mom.z);
@@ -392,31 +349,15 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             // whose cell lies outside the chunk
             float2 hax, hay, haz, cbx, cby, cbz;
             {
-#if PUSH3_DUAL
-                const unsigned sa = sm_ip + (inA ? oA * 80u : 0u), sb = sm_ip + (inB ? oB * 80u : 0u);
-                const float* ga = a.ip + (long long)cA * 20;
-                const float* gb = a.ip + (long long)cB * 20;
-                float fA[20], fB[20];
-#define CPIC_LDI(f, in, sx, gx)                                                                    \
-                *reinterpret_cast<float4*>(&f[0]) = ld_interp<0>(in, sx, gx);                        \
-                *reinterpret_cast<float4*>(&f[4]) = ld_interp<16>(in, sx, gx);                       \
-                *reinterpret_cast<float4*>(&f[8]) = ld_interp<32>(in, sx, gx);                       \
-                *reinterpret_cast<float4*>(&f[12]) = ld_interp<48>(in, sx, gx);                      \
-                *reinterpret_cast<float4*>(&f[16]) = ld_interp<64>(in, sx, gx);
-                CPIC_LDI(fA, inA, sa, ga)
-                CPIC_LDI(fB, inB, sb, gb)
-#undef CPIC_LDI
-#else
-                const float4* pa = ginA ? reinterpret_cast<const float4*>(sm.ip + oA_ * 20u)
+                const float4* pa = inA ? reinterpret_cast<const float4*>(sm.ip + oA * 20u)
                                         : reinterpret_cast<const float4*>(a.ip + (long long)cA * 20);
-                const float4* pb = ginB ? reinterpret_cast<const float4*>(sm.ip + oB_ * 20u)
+                const float4* pb = inB ? reinterpret_cast<const float4*>(sm.ip + oB * 20u)
                                         : reinterpret_cast<const float4*>(a.ip + (long long)cB * 20);
                 float fA[20], fB[20];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) *reinterpret_cast<float4*>(&fA[4 * k]) = pa[k];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) *reinterpret_cast<float4*>(&fB[4 * k]) = pb[k];
-#endif
 #define F2(k) make_float2(fA[k], fB[k])
                 hax = P.mul(P.madd<FMA>(z, P.madd<FMA>(y, F2(I_D2EXDYDZ), F2(I_DEXDZ)), P.madd<FMA>(y, F2(I_DEXDY), F2(I_EX))), a.qdt_2mc);
                 hay = P.mul(P.madd<FMA>(x, P.madd<FMA>(z, F2(I_D2EYDZDX), F2(I_DEYDX)), P.madd<FMA>(z, F2(I_DEYDZ), F2(I_EY))), a.qdt_2mc);
@@ -453,13 +394,6 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             uz = P.madd<FMA>(v4, P.mdiff<FMA>(v0, cby, v1, cbx), uz);
             ux = P.add(ux, hax); uy = P.add(uy, hay); uz = P.add(uz, haz);
             const float2 pux = ux, puy = uy, puz = uz;      // the new momentum (:165-167)
-#if PUSH3_LATEPF
-            {   // the next tile's records: requested now that the interpolator registers are free, consumed next iteration
-                const unsigned nA = iA + 64u;
-                if (nA < r1) rA_n = grec[nA];
-                if (nA + 1u < r1) rB_n = grec[nA + 1u];
-            }
-#endif
 
             // ---- displacement (src/push.h:169-182)
             {
@@ -484,12 +418,12 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             // a stayer's whole record in one full-sector store (a mover's is written by the drain)
             {
                 PRec<float> o;
-                if (stayA && !(PUSH3_KO && (ko & 1))) {
+                if (stayA) {
                     o.pos.x = nx_.x; o.pos.y = ny_.x; o.pos.z = nz_.x; o.pos.w = cell_to_real(cA, 0.f);
                     o.mom.x = pux.x; o.mom.y = puy.x; o.mom.z = puz.x; o.mom.w = w.x;
                     a.dst.rec[dA] = o;
                 }
-                if (stayB && !(PUSH3_KO && (ko & 1))) {
+                if (stayB) {
                     o.pos.x = nx_.y; o.pos.y = ny_.y; o.pos.z = nz_.y; o.pos.w = cell_to_real(cB, 0.f);
                     o.mom.x = pux.y; o.mom.y = puy.y; o.mom.z = puz.y; o.mom.w = w.y;
                     a.dst.rec[dB] = o;
@@ -516,7 +450,7 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                 rcell[lane] = nsA ? cA : (pairB ? cB : -1);
                 rcnt[lane] = (nsA ? 1 : 0) + (pairB ? 1 : 0);
                 // everything else that stays deposits directly: foreigners, and a native B whose pair straddles two cells
-                const bool dirA = stayA && !nsA && !(PUSH3_KO && (ko & 4)), dirB = stayB && !pairB && !(PUSH3_KO && (ko & 4));
+                const bool dirA = stayA && !nsA, dirB = stayB && !pairB;
                 float* const ga = a.acc + (long long)cA * 12;
                 float* const gb = a.acc + (long long)cB * 12;
                 red_add_v4_if(dirA, ga + 0, cur[0].x, cur[1].x, cur[2].x, cur[3].x);
@@ -528,11 +462,11 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                 red_add_v4_if(dirB, gb + 8, cur[8].y, cur[9].y, cur[10].y, cur[11].y);
                 red_add_u32_if(dirB, a.hist + cB, 1u);
                 __syncwarp();
-                if (!(PUSH3_KO && (ko & 8))) segsum_rows3(rows, rcell, rcnt, a.acc, a.hist, lane);
+                segsum_rows3(rows, rcell, rcnt, a.acc, a.hist, lane);
             }
 
             // ---- movers: append to the warp's list, drain densely (src/push.h:261-269 -> move_p)
-            const unsigned mA = (PUSH3_KO && (ko & 2)) ? 0u : __ballot_sync(full, movA), mB = (PUSH3_KO && (ko & 2)) ? 0u : __ballot_sync(full, movB);
+            const unsigned mA = __ballot_sync(full, movA), mB = __ballot_sync(full, movB);
             if (mA | mB) {
                 if (STATS) n_mov += (movA ? 1 : 0) + (movB ? 1 : 0);
                 if (mA) {
@@ -546,7 +480,7 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                     __syncwarp();
                     if (nlist >= 32) {
                         nlist -= 32;
-                        drain_movers3<FMA, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap, ko);
+                        drain_movers3<FMA, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap);
                     }
                 }
                 if (mB) {
@@ -560,14 +494,14 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                     __syncwarp();
                     if (nlist >= 32) {
                         nlist -= 32;
-                        drain_movers3<FMA, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap, ko);
+                        drain_movers3<FMA, STATS>(a, ml, nlist, 32, lane, n_cross, n_wrap);
                     }
                 }
             }
             rA = rA_n; rB = rB_n;
         }
     }
-    if (nlist > 0) drain_movers3<FMA, STATS>(a, ml, 0, nlist, lane, n_cross, n_wrap, ko);
+    if (nlist > 0) drain_movers3<FMA, STATS>(a, ml, 0, nlist, lane, n_cross, n_wrap);
 
     if (STATS) {
         __syncwarp();

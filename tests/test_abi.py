@@ -74,3 +74,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("the oracle", "").replace("CPU oracle", ""), f
+
+
+def test_benched_kernel_sass_matches_the_recorded_hash():
+    """The SASS of the benched k_push3 instantiation in the in-tree library equals the hash recorded next to the profiles
+    (profiles/k_push3_sass.md5, written by `tools/sass_hash.sh record`): what was measured is what ships, and a build with
+    a developer flag left on (tools/variants/*.patch) cannot slip in unnoticed."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    want = open(os.path.join(root, "profiles", "k_push3_sass.md5")).read().strip()
+    got = subprocess.run([os.path.join(root, "tools", "sass_hash.sh")], capture_output=True, text=True).stdout.strip()
+    assert got == want, "k_push3 SASS changed: re-measure, then tools/sass_hash.sh record"
