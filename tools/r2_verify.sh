@@ -7,10 +7,10 @@ timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
 echo "== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 echo "== bench (default)"
-timeout 900 python bench.py > gpurun_out/c18_bench_n1.json 2> gpurun_out/c18_bench.err; tail -2 gpurun_out/c18_bench.err | cut -c1-300
+timeout 900 python bench.py > gpurun_out/verify_bench_n1.json 2> gpurun_out/verify_bench.err; tail -2 gpurun_out/verify_bench.err | cut -c1-300
 python - <<PY
 import json
-for l in open("gpurun_out/c18_bench_n1.json"):
+for l in open("gpurun_out/verify_bench_n1.json"):
     if l.startswith("{"):
         d = json.loads(l)
         print(json.dumps({k: d[k] for k in ("value", "ms_per_step", "gpu_launches", "clocks")}))
@@ -21,4 +21,4 @@ for l in open("gpurun_out/c18_bench_n1.json"):
 PY
 echo "== reference arm"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | cut -c1-600
-} 2>&1 | tee gpurun_out/c18.log
+} 2>&1 | tee gpurun_out/verify.log
