@@ -9,7 +9,7 @@ The Python modules are plumbing for tests and the benchmark:
 * ``sim``    host-side mirror of the reference driver loop (``Simulation``);
 * ``dist``   multi-GPU modes (replicated grid / z-slabs) over ``torch.distributed``.
 """
-from ._lib import (BOUNDARY_PERIODIC, BOUNDARY_REFLECT, DEPOSIT_ATOMIC, DEPOSIT_ATOMIC_V4, DEPOSIT_AUTO,
+from ._lib import (BOUNDARY_PERIODIC, BOUNDARY_REFLECT, DEPOSIT_ATOMIC, DEPOSIT_ATOMIC_V4, DEPOSIT_AUTO, DEPOSIT_ORDERED,
                    DEPOSIT_WARP, FP_CONTRACT, FP_STRICT, SOLVER_EM, SOLVER_ES_1D, SORT_FUSED, Consts, Context, CpicError,
                    MGPU_AUTO, MGPU_REPLICATED, MGPU_SLAB, Mgpu, build, lib)
 from .decks import Deck
@@ -17,4 +17,4 @@ from .sim import Simulation
 
 __all__ = ["Context", "Consts", "CpicError", "Deck", "Simulation", "build", "lib", "SOLVER_EM", "SOLVER_ES_1D",
            "BOUNDARY_PERIODIC", "BOUNDARY_REFLECT", "FP_STRICT", "FP_CONTRACT", "DEPOSIT_AUTO", "DEPOSIT_ATOMIC",
-           "DEPOSIT_ATOMIC_V4", "DEPOSIT_WARP", "SORT_FUSED", "Mgpu", "MGPU_AUTO", "MGPU_REPLICATED", "MGPU_SLAB"]
+           "DEPOSIT_ATOMIC_V4", "DEPOSIT_WARP", "DEPOSIT_ORDERED", "SORT_FUSED", "Mgpu", "MGPU_AUTO", "MGPU_REPLICATED", "MGPU_SLAB"]

@@ -24,7 +24,7 @@ FIELD_NAMES = "ex ey ez cbx cby cbz jfx jfy jfz".split()
 SOLVER_EM, SOLVER_ES_1D = 0, 1
 BOUNDARY_REFLECT, BOUNDARY_PERIODIC = 0, 1
 FP_STRICT, FP_CONTRACT = 0, 1
-DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_ATOMIC_V4, DEPOSIT_WARP = 0, 1, 2, 3
+DEPOSIT_AUTO, DEPOSIT_ATOMIC, DEPOSIT_ATOMIC_V4, DEPOSIT_WARP, DEPOSIT_ORDERED = 0, 1, 2, 3, 4
 SORT_FUSED = -1      # cpic_step sort_interval: keep the store cell-ordered with the reordering push
 
 ERROR_NAMES = {-1: "CPIC_E_INVALID", -2: "CPIC_E_CUDA", -3: "CPIC_E_NOMEM", -4: "CPIC_E_CAPACITY",

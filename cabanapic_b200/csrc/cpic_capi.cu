@@ -4,6 +4,7 @@
 #include "../../include/cabanapic_b200.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdarg>
@@ -159,6 +160,7 @@ struct Ctx final : CtxBase {
             cudaFree(pbuf[0]); cudaFree(pbuf[1]); cudaFree(xfer);
             if (!parent) { cudaFree(fields); cudaFree(interp); cudaFree(acc); }
             cudaFree(seg[0]); cudaFree(seg[1]); cudaFree(cursor3); cudaFree(work3); cudaFree(cell_count); cudaFree(cell_count2); cudaFree(scan_l1); cudaFree(scan_l2); cudaFree(bad); cudaFree(en_dev); cudaFree(stats); cudaFree(mig_counters); cudaFree(mig_lists); cudaFree(leave_list); cudaFree(leave_count); cudaFree(dc);
+            cudaFree(ev_cell); cudaFree(ev_row); cudaFree(ev_keys); cudaFree(ev_order[0]); cudaFree(ev_order[1]); cudaFree(ev_tmp); cudaFree(ev_overflow);
             for (auto b : hs_buf) cudaFree(b);
             for (auto e : hs_ev) if (e) cudaEventDestroy(e);
             if (hs_up) cudaStreamDestroy(hs_up);
@@ -875,6 +877,7 @@ struct Ctx final : CtxBase {
         a.leave_list = nullptr; a.leave_count = nullptr; a.leave_cap = 0; a.leave_lo = 0; a.leave_hi = 0; a.leave_off = 0;
         a.dep_thresh = dep_thresh; a.dep_rounds = dep_rounds;
         a.np_dev = nullptr;
+        a.ev_cell = nullptr; a.ev_row = nullptr; a.ev_k = 0; a.ev_overflow = nullptr;
         a.priv_nc = use_priv() ? (int)g.nc : 0;
         return a;
     }
@@ -882,6 +885,7 @@ struct Ctx final : CtxBase {
         if (np == 0) return CPIC_OK;
         PushArgs<R> a;
         a.np_dev = nullptr; a.priv_nc = use_priv() ? (int)g.nc : 0;
+        a.ev_cell = nullptr; a.ev_row = nullptr; a.ev_k = 0; a.ev_overflow = nullptr;
         a.dst = P[cur]; a.cursor = nullptr;
         a.p = P[cur]; a.np = np; a.ip = interp; a.acc = acc;
         a.qdt_2mc = (R)k.qdt_2mc; a.cdt_dx = (R)k.cdt_dx; a.cdt_dy = (R)k.cdt_dy; a.cdt_dz = (R)k.cdt_dz; a.qsp = (R)k.qsp;
@@ -925,7 +929,56 @@ struct Ctx final : CtxBase {
         }
         if (dep == CPIC_DEPOSIT_ATOMIC) return fma ? launch_push<true, 1>(a) : launch_push<false, 1>(a);
         if (dep == CPIC_DEPOSIT_ATOMIC_V4) return fma ? launch_push<true, 2>(a) : launch_push<false, 2>(a);
+        if (dep == CPIC_DEPOSIT_ORDERED) return ordered_push(a, fma);
         return fma ? launch_push<true, 3>(a) : launch_push<false, 3>(a);
+    }
+    // CPIC_DEPOSIT_ORDERED (parity runs): the push records every streak (cell + 12 currents) as event (particle, streak);
+    // a stable radix sort of the event indices by cell (cub) makes each cell's events contiguous in (particle, streak)
+    // order, and k_ordered_accumulate adds them to the accumulator in that order -- the reference's serial summation
+    // order (src/push.h:218-254, src/move_p.h:154-190), hence bit-identical accumulators in strict FP mode.
+    static constexpr int EV_K = 8;                  // streaks per particle (1 + face crossings of one step)
+    static constexpr long long EV_MAX_NP = 1ll << 22;
+    int* ev_cell = nullptr;
+    R* ev_row = nullptr;
+    unsigned *ev_keys = nullptr, *ev_order[2] = {nullptr, nullptr}, *ev_overflow = nullptr;
+    void* ev_tmp = nullptr;
+    size_t ev_tmp_bytes = 0;
+    long long ev_cap = 0;
+    int ordered_push(PushArgs<R> a, bool fma) {
+        int rc;
+        if (a.np > EV_MAX_NP) return fail(CPIC_E_CAPACITY, "CPIC_DEPOSIT_ORDERED: %lld particles in one push exceed the mode's limit %lld", (long long)a.np, EV_MAX_NP);
+        const long long m = (long long)a.np * EV_K;
+        if (m > ev_cap) {
+            cudaFree(ev_cell); cudaFree(ev_row); cudaFree(ev_keys); cudaFree(ev_order[0]); cudaFree(ev_order[1]); cudaFree(ev_tmp);
+            ev_cell = nullptr; ev_row = nullptr; ev_keys = nullptr; ev_order[0] = ev_order[1] = nullptr; ev_tmp = nullptr; ev_cap = 0;
+            if ((rc = cuda(cudaMalloc(&ev_cell, (size_t)m * sizeof(int)), "cudaMalloc(event cells)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&ev_row, (size_t)m * 12 * sizeof(R)), "cudaMalloc(event rows)"))) return rc;
+            if ((rc = cuda(cudaMalloc(&ev_keys, (size_t)m * sizeof(unsigned)), "cudaMalloc(event keys)"))) return rc;
+            for (auto& o : ev_order)
+                if ((rc = cuda(cudaMalloc(&o, (size_t)m * sizeof(unsigned)), "cudaMalloc(event order)"))) return rc;
+            ev_tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, ev_tmp_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr,
+                                            (unsigned*)nullptr, (int)m, 0, 32, stream);
+            if ((rc = cuda(cudaMalloc(&ev_tmp, ev_tmp_bytes + 16), "cudaMalloc(sort scratch)"))) return rc;
+            ev_cap = m;
+        }
+        if (!ev_overflow && (rc = cuda(cudaMalloc(&ev_overflow, sizeof(unsigned)), "cudaMalloc"))) return rc;
+        cudaMemsetAsync(ev_cell, 0xff, (size_t)m * sizeof(int), stream);      // -1: unused (sorts behind every cell)
+        cudaMemsetAsync(ev_overflow, 0, sizeof(unsigned), stream);
+        a.ev_cell = ev_cell; a.ev_row = ev_row; a.ev_k = EV_K; a.ev_overflow = ev_overflow;
+        if ((rc = fma ? launch_push<true, 4>(a) : launch_push<false, 4>(a))) return rc;
+        k_iota<<<blocks_for(m), 256, 0, stream>>>(ev_order[0], m);
+        if ((rc = check_launch("k_iota"))) return rc;
+        size_t tb = ev_tmp_bytes;
+        if ((rc = cuda(cub::DeviceRadixSort::SortPairs(ev_tmp, tb, reinterpret_cast<const unsigned*>(ev_cell), ev_keys, ev_order[0], ev_order[1],
+                                                       (int)m, 0, 32, stream), "cub::DeviceRadixSort"))) return rc;
+        k_ordered_accumulate<R><<<blocks_for(g.nc * 12), 256, 0, stream>>>(ev_keys, ev_order[1], m, ev_row, acc, g.nc);
+        if ((rc = check_launch("k_ordered_accumulate"))) return rc;
+        unsigned over = 0;
+        if ((rc = cuda(cudaMemcpyAsync(&over, ev_overflow, sizeof over, cudaMemcpyDeviceToHost, stream), "D2H"))) return rc;
+        if ((rc = cuda(cudaStreamSynchronize(stream), "ordered deposit"))) return rc;
+        if (over) return fail(CPIC_E_CAPACITY, "CPIC_DEPOSIT_ORDERED: a particle crossed more than %d cell faces in one step", EV_K - 1);
+        return CPIC_OK;
     }
     // ------------------------------------------------------------------ host-resident step (cpic_step_host)
     // Three streams: `hs_up` carries the H2D copies of chunk i+1, the context's stream packs / pushes / unpacks
@@ -1214,7 +1267,7 @@ int validate(const cpic_params& p, std::string& why) {
     const long long nc = (long long)(p.nx + 2) * (p.ny + 2) * (p.nz + 2);
     if (nc > (1ll << 31) - 1) { snprintf(buf, sizeof buf, "%lld cells overflow the int cell index", nc); why = buf; return CPIC_E_INVALID; }
     if (p.fp_mode != CPIC_FP_STRICT && p.fp_mode != CPIC_FP_CONTRACT) { why = "unknown fp_mode"; return CPIC_E_INVALID; }
-    if (p.deposit_mode < 0 || p.deposit_mode > 3) { why = "unknown deposit_mode"; return CPIC_E_INVALID; }
+    if (p.deposit_mode < 0 || p.deposit_mode > CPIC_DEPOSIT_ORDERED) { why = "unknown deposit_mode"; return CPIC_E_INVALID; }
     return CPIC_OK;
 }
 
@@ -1583,7 +1636,7 @@ int cpic_append_particles_device(cpic_ctx* ctx, const void* buf, int64_t capacit
 
 int cpic_set_modes(cpic_ctx* ctx, int32_t fp_mode, int32_t deposit_mode) {
     CTX_HOSTNP(ctx);
-    if ((fp_mode != CPIC_FP_STRICT && fp_mode != CPIC_FP_CONTRACT) || deposit_mode < 0 || deposit_mode > 3)
+    if ((fp_mode != CPIC_FP_STRICT && fp_mode != CPIC_FP_CONTRACT) || deposit_mode < 0 || deposit_mode > CPIC_DEPOSIT_ORDERED)
         return c->fail(CPIC_E_INVALID, "set_modes: bad mode");
     c->prm.fp_mode = fp_mode;
     c->prm.deposit_mode = deposit_mode;

@@ -48,6 +48,13 @@ struct PushArgs {
     unsigned leave_cap;
     unsigned leave_off;        // added to the listed indices (a push over a sub-range of the store: cpic_step_host)
     int leave_lo, leave_hi;
+    // CPIC_DEPOSIT_ORDERED (k_push<DEPOSIT = 4>): nothing is added during the push; streak j of particle n writes its cell
+    // and its 12 currents to event n * ev_k + j, and k_ordered_accumulate adds the events of every cell in (particle,
+    // streak) order afterwards -- the order of the reference's serial loop
+    int* ev_cell;              // [np * ev_k], -1 = unused
+    R* ev_row;                 // [np * ev_k][12]
+    int ev_k;
+    unsigned* ev_overflow;     // set when a particle has more than ev_k streaks
     int priv_nc;               // > 0: k_push2<PRIV> keeps a block-private accumulator (+ histogram) of this many cells in shared memory
     const long long* np_dev;   // optional: the particle count lives on the device (overrides np; k_push2 only)
 };
@@ -161,6 +168,36 @@ __device__ __forceinline__ R warp_transpose_sum12(const R (&a)[12], int lane) {
     return r1;
 }
 
+// CPIC_DEPOSIT_ORDERED: record streak j of particle n
+template <class R>
+__device__ __forceinline__ void record_event(const PushArgs<R>& a, long long n, int j, int cell, const R (&cur)[12]) {
+    if (j >= a.ev_k) { *a.ev_overflow = 1u; return; }
+    const long long e = n * a.ev_k + j;
+    a.ev_cell[e] = cell;
+    R* row = a.ev_row + e * 12;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) row[k] = cur[k];
+}
+// one thread per (cell, entry): the events of the cell are contiguous in `order` (stable sort of the event indices by
+// cell), in (particle, streak) order; lo / hi by binary search in the sorted keys.  acc[c][k] = (..((acc + e0) + e1) + ..)
+template <class R>
+__global__ void __launch_bounds__(256) k_ordered_accumulate(const unsigned* __restrict__ keys, const unsigned* __restrict__ order,
+                                                            long long m, const R* __restrict__ ev_row, R* __restrict__ acc, long long nc) {
+    const long long t = blockIdx.x * 256LL + threadIdx.x;
+    if (t >= nc * 12) return;
+    const unsigned c = (unsigned)(t / 12);
+    const int k = (int)(t % 12);
+    long long lo = 0, hi = m;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (keys[mid] < c) lo = mid + 1; else hi = mid; }
+    R s = acc[t];
+    for (long long i = lo; i < m && keys[i] == c; ++i) s += ev_row[(long long)order[i] * 12 + k];
+    acc[t] = s;
+}
+__global__ void __launch_bounds__(256) k_iota(unsigned* v, long long n) {
+    const long long i = blockIdx.x * 256LL + threadIdx.x;
+    if (i < n) v[i] = (unsigned)i;
+}
+
 // First-streak deposit; must be called by all 32 lanes of the warp (converged).
 template <class R, int DEPOSIT>
 __device__ __forceinline__ void deposit_first(R* __restrict__ acc, bool valid, int ii, const R (&a)[12], int lane,
@@ -169,6 +206,8 @@ __device__ __forceinline__ void deposit_first(R* __restrict__ acc, bool valid, i
         if (valid) row_add_scalar(acc + (long long)ii * 12, a);
     } else if constexpr (DEPOSIT == 2) {
         if (valid) row_add_vec(acc + (long long)ii * 12, a);
+    } else if constexpr (DEPOSIT == 4) {
+        // (ordered mode: the caller records the event instead)
     } else {
         const unsigned full = 0xffffffffu;
         const unsigned vmask = __ballot_sync(full, valid);
@@ -364,12 +403,15 @@ __device__ __forceinline__ void drain_movers(const PushArgs<R>& a, List& ml, int
         const R qq = ml.q[m];
         int c = ml.cell[m];
         unsigned flip = 0;
+        int streak = 0;
         for (;;) {
             R sx, sy, sz, mx, my, mz, v5, dirv;
             const int axis = mover_streak(px, py, pz, dx, dy, dz, qq, sx, sy, sz, mx, my, mz, v5, dirv);
             R jc[12];
             streak_currents<FMA>(qq, sx, sy, sz, mx, my, mz, v5, jc);
-            if constexpr (PRIV) {
+            if constexpr (DEPOSIT == 4) {
+                record_event(a, (long long)ml.idx[m], streak++, c, jc);
+            } else if constexpr (PRIV) {
                 acc_add4<true>(nullptr, sacc, c, 0, (float)jc[0], (float)jc[1], (float)jc[2], (float)jc[3]);
                 acc_add4<true>(nullptr, sacc, c, 1, (float)jc[4], (float)jc[5], (float)jc[6], (float)jc[7]);
                 acc_add4<true>(nullptr, sacc, c, 2, (float)jc[8], (float)jc[9], (float)jc[10], (float)jc[11]);
@@ -519,7 +561,8 @@ k_push(PushArgs<R> a) {
         }
 
         // in-cell particles: one streak into the particle's own cell
-        deposit_first<R, DEPOSIT>(a.acc, stay, ii, cur, lane, a.dep_thresh, a.dep_rounds);
+        if constexpr (DEPOSIT == 4) { if (stay) record_event(a, n, 0, ii, cur); }
+        else deposit_first<R, DEPOSIT>(a.acc, stay, ii, cur, lane, a.dep_thresh, a.dep_rounds);
 
         // movers: append to the warp's list (warp-synchronous, no atomics)
         const unsigned mm = __ballot_sync(0xffffffffu, mover);

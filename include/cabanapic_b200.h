@@ -69,7 +69,12 @@ enum {
     CPIC_DEPOSIT_AUTO = 0,        /* = WARP                                               */
     CPIC_DEPOSIT_ATOMIC = 1,      /* 12 scalar global atomics per streak                  */
     CPIC_DEPOSIT_ATOMIC_V4 = 2,   /* 3 x 128-bit vector atomics per streak (float only)   */
-    CPIC_DEPOSIT_WARP = 3         /* warp-aggregated per cell, then one atomic row/warp   */
+    CPIC_DEPOSIT_WARP = 3,        /* warp-aggregated per cell, then one atomic row/warp   */
+    CPIC_DEPOSIT_ORDERED = 4      /* parity runs: every streak is recorded and the streaks of a cell are added in (particle,
+                                     streak) order -- the summation order of the reference's serial loop (src/push.h:218-254,
+                                     src/move_p.h:154-190), so accumulators, J and whole histories are bit-identical to it in
+                                     strict FP mode.  In-place push only (the particle order must be the reference's), at most
+                                     2^22 particles, not fast.                            */
 };
 
 typedef struct cpic_ctx cpic_ctx;
