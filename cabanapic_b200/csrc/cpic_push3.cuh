@@ -304,14 +304,19 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
         for (unsigned i0 = r0; i0 < r1; i0 += 64u) {
             const unsigned iA = i0 + 2u * lane, iB = iA + 1u;
             const bool validA = iA < r1, validB = iB < r1;
-            PRec<float> rA_n = rzero, rB_n = rzero;
-            {   // the next tile's records: requested now, consumed next iteration (nothing may touch them before)
-                const unsigned nA = iA + 64u;
-                if (nA < r1) rA_n = grec[nA];
-                if (nA + 1u < r1) rB_n = grec[nA + 1u];
-            }
+            // unpack this tile's records into the packed operands, then request the next tile's records INTO THE SAME
+            // REGISTERS (consumed next iteration; nothing may touch them before).  No second record buffer, no copy at the
+            // end of the iteration; a lane without a next particle keeps its old, finite record (it is masked by valid*).
             const int cA = validA ? real_to_cell(rA.pos.w) : c0;
             const int cB = validB ? real_to_cell(rB.pos.w) : cA;
+            float2 x = make_float2(rA.pos.x, rB.pos.x), y = make_float2(rA.pos.y, rB.pos.y), z = make_float2(rA.pos.z, rB.pos.z);
+            float2 ux = make_float2(rA.mom.x, rB.mom.x), uy = make_float2(rA.mom.y, rB.mom.y), uz = make_float2(rA.mom.z, rB.mom.z);
+            const float2 w = make_float2(rA.mom.w, rB.mom.w);
+            {
+                const unsigned nA = iA + 64u;
+                if (nA < r1) rA = grec[nA];
+                if (nA + 1u < r1) rB = grec[nA + 1u];
+            }
             const unsigned oA = (unsigned)(cA - c0), oB = (unsigned)(cB - c0);
             const bool inA = oA < (unsigned)chn, inB = oB < (unsigned)chn;
             // native: the particle's index lies inside the segment of its own cell
@@ -340,10 +345,6 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
             if (mycnt) base = atomicAdd(a.cursor + cf + lane, mycnt);
             if (forA) fsA = atomicAdd(a.cursor + cA, 1u);
             if (forB) fsB = atomicAdd(a.cursor + cB, 1u);
-
-            float2 x = make_float2(rA.pos.x, rB.pos.x), y = make_float2(rA.pos.y, rB.pos.y), z = make_float2(rA.pos.z, rB.pos.z);
-            float2 ux = make_float2(rA.mom.x, rB.mom.x), uy = make_float2(rA.mom.y, rB.mom.y), uz = make_float2(rA.mom.z, rB.mom.z);
-            const float2 w = make_float2(rA.mom.w, rB.mom.w);
 
             // ---- field gather (src/push.h:74-138): from the TMA-staged chunk, or from global memory for a foreigner
             // whose cell lies outside the chunk
@@ -498,7 +499,6 @@ __global__ void __launch_bounds__(PUSH3_WARPS * 32, PUSH3_MIN_BLOCKS) k_push3(co
                     }
                 }
             }
-            rA = rA_n; rB = rB_n;
         }
     }
     if (nlist > 0) drain_movers3<FMA, STATS>(a, ml, 0, nlist, lane, n_cross, n_wrap);
