@@ -109,6 +109,9 @@ struct CtxBase {
     virtual bool is_species_of(const CtxBase* p) const = 0;
     virtual int sync_np() = 0;      // device-count mode -> host-count mode (synchronises); no-op otherwise
     virtual long long* device_counts() = 0;      // dc (may be null before the first device-counted migration)
+    // which of the double buffers (particle store, segment bounds, cell counts) are current: a captured pair of steps
+    // bakes these in, so a graph may only be replayed from the state it was captured in
+    virtual unsigned state_signature() const = 0;
     long long fb_steps = 0;         // steps taken in the few-cells fallback of CPIC_SORT_FUSED (sort when % 8 == 0)
     bool dev_count = false;         // slab mode: np lives in dc[0] on the device, the host's np is stale
     virtual int step_host(const cpic_consts& k, const void* const in[8], void* const out[8], long long n,
@@ -458,6 +461,9 @@ struct Ctx final : CtxBase {
     // ------------------------------------------------------------------ slab migration, counts on the device
     long long* dc = nullptr;            // [0] np [1] error flags [2] [3] leavers of the last extraction
     long long* device_counts() override { return dc; }
+    unsigned state_signature() const override {
+        return (unsigned)cur | ((unsigned)seg_cur << 1) | (cell_count < cell_count2 ? 4u : 0u) | (dev_count ? 8u : 0u) | (seg_valid ? 16u : 0u);
+    }
     int enter_dev_count() {
         if (dev_count) return CPIC_OK;
         int rc;

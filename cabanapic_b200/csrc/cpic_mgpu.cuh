@@ -210,6 +210,7 @@ struct Mgpu {
     cudaGraphExec_t gexec = nullptr;
     bool graph_failed = false, used_graph = false;
     cpic_consts graph_k{};
+    unsigned graph_sig = 0;      // CtxBase::state_signature() at capture time
     long long steps_done = 0;
 
     int fail(int code, const char* fmt, ...) {
@@ -609,6 +610,7 @@ struct Mgpu {
         cudaGraphDestroy(g);
         if (e != cudaSuccess) { gexec = nullptr; cudaGetLastError(); return fail(CPIC_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
         graph_k = k;
+        graph_sig = c->state_signature();      // (a pair of steps returns to this state)
         return CPIC_OK;
     }
     long long graph_launches = 0;
@@ -810,7 +812,9 @@ int cpic_mgpu_step(cpic_mgpu* mm, const cpic_consts* k, int64_t nsteps, int32_t 
         if (sort_interval != CPIC_SORT_FUSED) return m->fail(CPIC_E_UNSUPPORTED, "mgpu_step: slab mode runs the reordering push (sort_interval = CPIC_SORT_FUSED) only");
         int64_t s = 0;
         if (use_graph && !m->graph_failed && nsteps >= 2 && m->steps_done >= 2 && c->dev_count && c->seg_valid) {
-            if (m->gexec && !same_consts(*k, m->graph_k)) { cudaGraphExecDestroy(m->gexec); m->gexec = nullptr; }
+            // an odd number of eager steps (or a host-resident step) since the capture leaves the other halves of the
+            // double buffers current: the graph would read stale ones -- capture again
+            if (m->gexec && (!same_consts(*k, m->graph_k) || m->graph_sig != c->state_signature())) { cudaGraphExecDestroy(m->gexec); m->gexec = nullptr; }
             if (!m->gexec && (rc = m->capture_pair(*k))) {
                 fprintf(stderr, "[cabanapic_b200 rank %d] CUDA-graph capture of the slab step failed, running eagerly: %s\n", m->rank, m->err.c_str());
                 m->graph_failed = true;
@@ -861,7 +865,7 @@ int cpic_mgpu_prepare_graph(cpic_mgpu* mm, const cpic_consts* k) {
     CtxBase* c = m->c;
     if (m->mode != CPIC_MGPU_SLAB || (c->g.per & 4) || m->graph_failed || m->steps_done < 2 || !c->dev_count || !c->seg_valid)
         return m->fail(CPIC_E_UNSUPPORTED, "prepare_graph: needs slab mode after at least two eager fused steps");
-    if (m->gexec && same_consts(*k, m->graph_k)) return CPIC_OK;
+    if (m->gexec && same_consts(*k, m->graph_k) && m->graph_sig == c->state_signature()) return CPIC_OK;
     if (m->gexec) { cudaGraphExecDestroy(m->gexec); m->gexec = nullptr; }
     const int rc = m->capture_pair(*k);
     if (rc) m->graph_failed = true;

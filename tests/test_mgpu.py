@@ -72,6 +72,13 @@ def _worker(rank, world, idfile, outdir, mode, graph):
         assert m.ctx.num_particles == cnt
         host_p = {n: a[n][:cnt].copy() for n in PARTICLE_NAMES}
         host_f = fa.copy()
+    elif graph == "odd":                                 # an odd number of eager steps between two replays
+        m.step(k, 2, cp.SORT_FUSED, use_graph=True)      # eager (the graph path needs two steps behind it)
+        m.step(k, 2, cp.SORT_FUSED, use_graph=True)      # capture + replay
+        used = m.used_graph
+        m.step(k, 1, cp.SORT_FUSED, use_graph=True)      # eager: the other halves of the double buffers are current now
+        m.step(k, NSTEPS - 5, cp.SORT_FUSED, use_graph=True)   # must capture again, not replay the stale graph
+        used = used and m.used_graph
     elif graph:                                          # whole run in two calls: eager warm-up, then graph replay
         m.step(k, 3, cp.SORT_FUSED, use_graph=True)
         m.step(k, NSTEPS - 3, cp.SORT_FUSED, use_graph=True)
@@ -179,6 +186,18 @@ def test_native_slab_stepper_graph_replay(tmp_path):
     """The same run as two calls with use_graph: pairs of steps replayed from a CUDA graph (NCCL kernels, device-counted
     migration and the external timing events included) end in the same state."""
     world, got = _run(tmp_path, "slab", graph=True)
+    s, want_mig, _ = _oracle(world)
+    assert bool(got[0]["used"]), "the graph path was not taken"
+    for r in range(world):
+        assert np.array_equal(got[r]["tot"], want_mig[r].sum(axis=0))
+    _check_state(world, got, s)
+
+
+def test_native_slab_stepper_graph_replay_after_odd_eager_steps(tmp_path):
+    """A captured pair of steps bakes in which halves of the double buffers (particle store, segment bounds, cell counts)
+    are current.  After an odd number of eager steps the graph must be captured again (CtxBase::state_signature), not
+    replayed on stale buffers."""
+    world, got = _run(tmp_path, "slab", graph="odd")
     s, want_mig, _ = _oracle(world)
     assert bool(got[0]["used"]), "the graph path was not taken"
     for r in range(world):
