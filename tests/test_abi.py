@@ -88,3 +88,19 @@ def test_benched_kernel_sass_matches_the_recorded_hash():
     want = open(os.path.join(root, "profiles", "k_push3_sass.md5")).read().strip()
     got = subprocess.run([os.path.join(root, "tools", "sass_hash.sh")], capture_output=True, text=True).stdout.strip()
     assert got == want, "k_push3 SASS changed: re-measure, then tools/sass_hash.sh record"
+
+
+def test_variant_patches_apply_to_this_tree():
+    """tools/variants/*.patch (kernel variants that were measured and not adopted, developer instrumentation) are kept
+    applicable: the numbers in DESIGN.md that come from them stay reproducible."""
+    import glob
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("git") or not os.path.isdir(os.path.join(root, ".git")):
+        pytest.skip("not a git work tree")
+    patches = sorted(glob.glob(os.path.join(root, "tools", "variants", "*.patch")))
+    assert patches
+    for p in patches:
+        r = subprocess.run(["git", "apply", "--check", p], cwd=root, capture_output=True, text=True)
+        assert r.returncode == 0, (os.path.basename(p), r.stderr[-500:])
